@@ -1,0 +1,205 @@
+"""Python mirror of the C ABI (include/glio_b200.h) — a thin ctypes layer over glio_b200/libglio_b200.so.
+
+The method names follow the reference's own vocabulary (GLIO/src/Estimator.cpp): set_map ~ kd_tree->setInputCloud,
+assoc_scan_to_map ~ findCorrespondingSurfFeatures, select ~ featureSelection (as an input index list),
+eval_unary ~ ResidualBlock::Evaluate over LidarPlaneNormFactor + normal-equation accumulation.
+
+There is no CPU fallback: if the CUDA library is missing or no GPU is visible, construction raises.
+torch is used only for device buffers/streams by callers (bench.py); this module needs numpy + ctypes only.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libglio_b200.so")
+_LIB = None
+
+HOST, DEVICE = 0, 1
+MATCH_VALID, MATCH_FAIL_RADIUS, MATCH_FAIL_PLANE, MATCH_FAIL_WEIGHT = 0, 1, 2, 3
+
+
+class GlioError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("kd_max_radius", C.c_double), ("surf_dist_thres", C.c_double), ("lidar_const", C.c_double),
+                ("weight_min", C.c_double), ("huber_delta", C.c_double), ("q_lb", C.c_double * 4),
+                ("t_lb", C.c_double * 3), ("batch_max_radius", C.c_double), ("batch_dist_thres", C.c_double),
+                ("batch_score", C.c_double), ("cell_size", C.c_float), ("keep_debug", C.c_int32)]
+
+
+def lib():
+    """Load the CUDA library; raise loudly when it is not built (no fallback path exists)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_LIB_PATH):
+            raise GlioError(f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(glio_b200 has no CPU fallback)")
+        L = C.CDLL(_LIB_PATH)
+        L.glio_last_error.restype = C.c_char_p
+        L.glio_last_error.argtypes = [C.c_void_p]
+        L.glio_stream.restype = C.c_void_p
+        L.glio_stream.argtypes = [C.c_void_p]
+        L.glio_launch_count.restype = C.c_int64
+        L.glio_launch_count.argtypes = [C.c_void_p]
+        L.glio_destroy.argtypes = [C.c_void_p]
+        L.glio_destroy.restype = None
+        _LIB = L
+    return _LIB
+
+
+def default_params(**kw):
+    p = Params()
+    lib().glio_default_params(C.byref(p))
+    for k, v in kw.items():
+        if k in ("q_lb", "t_lb"):
+            arr = getattr(p, k)
+            for i, x in enumerate(v):
+                arr[i] = float(x)
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    raise TypeError(type(a))
+
+
+def _points_arg(xyz):
+    """numpy float32 (n,3|stride) host array, or (device_ptr:int, n, stride) tuple / torch tensor."""
+    if isinstance(xyz, np.ndarray):
+        a = np.ascontiguousarray(xyz, dtype=np.float32)
+        if a.ndim == 1:
+            a = a.reshape(-1, 3)
+        return a, _ptr(a), a.shape[0], a.shape[1], HOST
+    if hasattr(xyz, "data_ptr"):          # torch tensor on the GPU
+        assert xyz.is_cuda and xyz.is_contiguous() and xyz.dtype.itemsize == 4
+        return xyz, C.c_void_p(xyz.data_ptr()), xyz.shape[0], xyz.shape[1], DEVICE
+    raise TypeError("points must be a numpy array or a CUDA torch tensor")
+
+
+class Context:
+    def __init__(self, device=0, params=None, **kw):
+        self._lib = lib()
+        self.params = params if params is not None else default_params(**kw)
+        self._h = C.c_void_p()
+        rc = self._lib.glio_create(C.c_int(device), C.byref(self.params), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.glio_last_error(None)
+            raise GlioError(f"glio_create failed ({rc}): {msg.decode() if msg else ''}")
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.glio_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            msg = self._lib.glio_last_error(self._h)
+            raise GlioError(f"glio error {rc}: {msg.decode() if msg else ''}")
+
+    @property
+    def stream(self):
+        return self._lib.glio_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.glio_launch_count(self._h))
+
+    def synchronize(self):
+        self._chk(self._lib.glio_synchronize(self._h))
+
+    def lidar_pose(self, pose_body):
+        pb = np.ascontiguousarray(pose_body, np.float64)
+        t2 = np.zeros(3); q2 = np.zeros(4)
+        self._lib.glio_lidar_pose(C.byref(self.params), _ptr(pb), _ptr(t2), _ptr(q2))
+        return t2, q2
+
+    # ---- K0
+    def set_map(self, xyz):
+        keep, p, n, stride, mem = _points_arg(xyz)
+        self._map_keep = keep
+        self._chk(self._lib.glio_set_map(self._h, p, C.c_int64(n), C.c_int(stride), C.c_int(mem)))
+
+    # ---- K1
+    def assoc_scan_to_map(self, slot, scan_xyz, t, q):
+        keep, p, n, stride, mem = _points_arg(scan_xyz)
+        self._keep.append(keep); self._keep = self._keep[-64:]
+        t = np.ascontiguousarray(t, np.float64); q = np.ascontiguousarray(q, np.float64)
+        nm = C.c_int64(0)
+        self._chk(self._lib.glio_assoc_scan_to_map(self._h, C.c_int(slot), p, C.c_int64(n), C.c_int(stride), C.c_int(mem),
+                                                   _ptr(t), _ptr(q), C.byref(nm)))
+        return int(nm.value)
+
+    def window_set_scans(self, scans):
+        args = [_points_arg(s) for s in scans]
+        self._scan_keep = [a[0] for a in args]
+        W = len(args)
+        ptrs = (C.c_void_p * W)(*[a[1] for a in args])
+        Q = (C.c_int64 * W)(*[a[2] for a in args])
+        strides = {a[3] for a in args}; mems = {a[4] for a in args}
+        assert len(strides) == 1 and len(mems) == 1
+        self._chk(self._lib.glio_window_set_scans(self._h, C.c_int(W), ptrs, Q, C.c_int(strides.pop()), C.c_int(mems.pop())))
+
+    def window_associate(self, poses_body):
+        pb = np.ascontiguousarray(poses_body, np.float64).reshape(-1, 7)
+        W = len(pb)
+        nm = np.zeros(W, np.int64)
+        self._chk(self._lib.glio_window_associate(self._h, C.c_int(W), _ptr(pb), _ptr(nm)))
+        return nm
+
+    def get_matches(self, slot, capacity):
+        cp = np.empty((capacity, 3), np.float32); nsd = np.empty((capacity, 4), np.float32)
+        w = np.empty(capacity, np.float32); src = np.empty(capacity, np.int32)
+        n = C.c_int64(0)
+        self._chk(self._lib.glio_get_matches(self._h, C.c_int(slot), C.c_int64(capacity), _ptr(cp), _ptr(nsd), _ptr(w), _ptr(src), C.byref(n)))
+        n = int(n.value)
+        return dict(cp=cp[:n], nsd=nsd[:n], weight=w[:n], src=src[:n], n=n)
+
+    def get_assoc_debug(self, slot, Q):
+        out = dict(status=np.empty(Q, np.uint8), idx5=np.empty((Q, 5), np.int32), sqd5=np.empty((Q, 5), np.float32),
+                   pm=np.empty((Q, 3), np.float32), plane=np.empty((Q, 4), np.float64))
+        self._chk(self._lib.glio_get_assoc_debug(self._h, C.c_int(slot), C.c_int64(Q), _ptr(out["status"]), _ptr(out["idx5"]),
+                                                 _ptr(out["sqd5"]), _ptr(out["pm"]), _ptr(out["plane"])))
+        return out
+
+    def select(self, slot, keep):
+        if keep is None:
+            self._chk(self._lib.glio_select(self._h, C.c_int(slot), None, C.c_int64(-1)))
+            return
+        k = np.ascontiguousarray(keep, np.int32)
+        self._chk(self._lib.glio_select(self._h, C.c_int(slot), _ptr(k), C.c_int64(len(k))))
+
+    # ---- K2
+    def eval_unary(self, poses_body, jac_kind=0, want_jac=True):
+        pb = np.ascontiguousarray(poses_body, np.float64).reshape(-1, 7)
+        W = len(pb)
+        H = np.zeros((W, 6, 6)) if want_jac else None
+        g = np.zeros((W, 6)) if want_jac else None
+        cost = np.zeros(W)
+        self._chk(self._lib.glio_eval_unary(self._h, C.c_int(W), _ptr(pb), C.c_int(jac_kind), _ptr(H), _ptr(g), _ptr(cost)))
+        return dict(H=H, g=g, cost=cost)
+
+    def eval_unary_residuals(self, slot, pose_body, capacity, jac_kind=0):
+        pb = np.ascontiguousarray(pose_body, np.float64)
+        r = np.empty(capacity); J = np.empty((capacity, 6)); n = C.c_int64(0)
+        self._chk(self._lib.glio_eval_unary_residuals(self._h, C.c_int(slot), _ptr(pb), C.c_int(jac_kind), C.c_int64(capacity),
+                                                      _ptr(r), _ptr(J), C.byref(n)))
+        n = int(n.value)
+        return r[:n], J[:n]

@@ -1,0 +1,450 @@
+// capi.cu — the extern "C" boundary (include/glio_b200.h) and the context that owns device state.
+// No CPU fallback: without a CUDA device glio_create fails.
+#include <array>
+#include <map>
+#include <memory>
+
+#include "common.cuh"
+#include "hostmath.h"
+
+using namespace glio;
+
+namespace {
+
+struct Slot {
+  int64_t Q = 0;
+  int stride = 3;
+  DevBuf<float> scan;            // device copy of the scan (stride floats per point)
+  const float* scan_ptr = nullptr;  // == scan.p, or a caller-owned device pointer (GLIO_DEVICE input)
+  DevBuf<float4> m_cpw, m_nsd;   // compacted matches, scan order
+  DevBuf<int32_t> m_src;
+  int64_t n_match = 0;
+  DevBuf<float4> s_cpw, s_nsd;   // selected subset
+  int64_t n_sel = -1;            // -1: no selection -> all matches are active
+  // debug (keep_debug)
+  DevBuf<uint8_t> dbg_status;
+  DevBuf<int32_t> dbg_idx5;
+  DevBuf<float> dbg_sqd5;
+  DevBuf<float4> dbg_pm;
+  DevBuf<double> dbg_plane;
+  int64_t dbg_Q = 0;
+  void release() {
+    scan.release(); m_cpw.release(); m_nsd.release(); m_src.release(); s_cpw.release(); s_nsd.release();
+    dbg_status.release(); dbg_idx5.release(); dbg_sqd5.release(); dbg_pm.release(); dbg_plane.release();
+  }
+};
+
+}  // namespace
+
+struct glio_ctx {
+  int device = 0;
+  cudaStream_t st = nullptr;
+  glio_params prm{};
+  std::string err;
+  LaunchCounter lc;
+
+  GridBuild map;
+  bool has_map = false;
+  DevBuf<float> map_stage;
+
+  std::vector<std::unique_ptr<Slot>> slots;
+
+  // association workspace
+  DevBuf<float4> w_pm, w_nsd;
+  DevBuf<uint16_t> w_seg;
+  DevBuf<uint32_t> w_order;
+  DevBuf<uint8_t> w_status;
+  DevBuf<float> w_weight;
+  DevBuf<double> w_nc, w_plane;
+  DevBuf<int32_t> w_idx5;
+  DevBuf<float> w_sqd5;
+  DevBuf<int> w_flags, w_pos, cell_count, cell_pos, scan_tmp;
+  DevBuf<SegDesc> d_segs;
+  DevBuf<CompactDst> d_dst;
+  DevBuf<int> d_counts;
+  PinnedBuf<int> h_counts;
+  DevBuf<int> d_bad;
+  DevBuf<int32_t> d_keep;
+
+  // evaluation
+  DevBuf<EvalItem> d_items;
+  DevBuf<int> d_kf_item_start;
+  DevBuf<double> d_partials, d_out, d_poses, d_r, d_J;
+  PinnedBuf<double> h_out, h_poses;
+  DevBuf<unsigned int> d_ticket;
+  bool items_dirty = true;
+  int items_W = -1;
+  int n_items = 0;
+
+  Slot& slot(int k) {
+    GLIO_REQUIRE(k >= 0 && k < 4096, GLIO_ERR_ARG, "slot index out of range");
+    if ((size_t)k >= slots.size()) slots.resize((size_t)k + 1);
+    if (!slots[k]) slots[k].reset(new Slot());
+    return *slots[k];
+  }
+};
+
+namespace {
+
+thread_local std::string tl_err;
+
+template <class F>
+int guarded(glio_ctx* ctx, F&& f) {
+  try {
+    if (ctx) GLIO_CUDA_TRY(cudaSetDevice(ctx->device));
+    f();
+    return GLIO_OK;
+  } catch (const Error& e) {
+    if (ctx) ctx->err = e.msg;
+    tl_err = e.msg; set_global_error(e.msg);
+    return e.code;
+  } catch (const std::exception& e) {
+    if (ctx) ctx->err = e.what();
+    tl_err = e.what(); set_global_error(e.what());
+    return GLIO_ERR_STATE;
+  }
+}
+
+// bring `n` points (stride floats each) to the device; returns the device pointer to read from
+const float* stage_points(glio_ctx* c, DevBuf<float>& buf, const float* xyz, int64_t n, int stride, int mem) {
+  GLIO_REQUIRE(xyz != nullptr && n > 0, GLIO_ERR_ARG, "null or empty point array");
+  GLIO_REQUIRE(stride >= 3 && stride <= 64, GLIO_ERR_ARG, "stride_floats must be in [3,64]");
+  if (mem == GLIO_DEVICE) return xyz;
+  buf.reserve((size_t)n * stride);
+  GLIO_CUDA_TRY(cudaMemcpyAsync(buf.p, xyz, (size_t)n * stride * sizeof(float), cudaMemcpyHostToDevice, c->st));
+  return buf.p;
+}
+
+void ensure_work(glio_ctx* c, int64_t Qt, bool pair) {
+  c->w_pm.reserve((size_t)Qt); c->w_seg.reserve((size_t)Qt); c->w_order.reserve((size_t)Qt);
+  c->w_status.reserve((size_t)Qt); c->w_weight.reserve((size_t)Qt);
+  c->w_flags.reserve((size_t)Qt + 1); c->w_pos.reserve((size_t)Qt + 1);
+  if (pair) c->w_nc.reserve((size_t)Qt * 6); else c->w_nsd.reserve((size_t)Qt);
+  if (c->prm.keep_debug) { c->w_idx5.reserve((size_t)Qt * 5); c->w_sqd5.reserve((size_t)Qt * 5); c->w_plane.reserve((size_t)Qt * 4); }
+}
+
+AssocWork make_work(glio_ctx* c, int64_t Qt, bool pair) {
+  AssocWork w{};
+  w.Qt = Qt; w.pm = c->w_pm.p; w.seg = c->w_seg.p; w.order = c->w_order.p; w.status = c->w_status.p;
+  w.nsd = pair ? nullptr : c->w_nsd.p; w.weight = c->w_weight.p; w.normal_cent = pair ? c->w_nc.p : nullptr;
+  if (c->prm.keep_debug) { w.idx5 = c->w_idx5.p; w.sqd5 = c->w_sqd5.p; w.plane = c->w_plane.p; }
+  return w;
+}
+
+// run scan-to-map association for the given slots (one launch), compact, fetch counts
+void associate_slots(glio_ctx* c, const std::vector<int>& ids, const std::vector<std::array<double, 7>>& lidar_poses,
+                     int64_t* n_match) {
+  GLIO_REQUIRE(c->has_map, GLIO_ERR_STATE, "glio_set_map must be called before association");
+  const int nseg = (int)ids.size();
+  std::vector<SegDesc> segs(nseg);
+  std::vector<CompactDst> dst(nseg);
+  int64_t Qt = 0;
+  for (int s = 0; s < nseg; ++s) {
+    Slot& sl = c->slot(ids[s]);
+    GLIO_REQUIRE(sl.Q > 0 && sl.scan_ptr, GLIO_ERR_STATE, "slot has no scan");
+    segs[s].src = sl.scan_ptr; segs[s].stride = sl.stride; segs[s].count = sl.Q; segs[s].offset = Qt;
+    for (int k = 0; k < 3; ++k) segs[s].t[k] = lidar_poses[s][k];
+    for (int k = 0; k < 4; ++k) segs[s].q[k] = lidar_poses[s][3 + k];
+    sl.m_cpw.reserve((size_t)sl.Q); sl.m_nsd.reserve((size_t)sl.Q); sl.m_src.reserve((size_t)sl.Q);
+    dst[s].cpw = sl.m_cpw.p; dst[s].nsd = sl.m_nsd.p; dst[s].nc = nullptr; dst[s].src = sl.m_src.p;
+    sl.n_sel = -1;
+    Qt += sl.Q;
+  }
+  ensure_work(c, Qt, false);
+  c->d_segs.reserve(nseg); c->d_dst.reserve(nseg); c->d_counts.reserve(nseg); c->h_counts.reserve(nseg);
+  GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_segs.p, segs.data(), nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, c->st));
+  GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_dst.p, dst.data(), nseg * sizeof(CompactDst), cudaMemcpyHostToDevice, c->st));
+  AssocWork w = make_work(c, Qt, false);
+  AssocGates gates{c->prm.kd_max_radius, c->prm.surf_dist_thres, c->prm.weight_min};
+  assoc_run(c->map, c->d_segs.p, nseg, w, gates, nullptr, 0, c->cell_count, c->cell_pos, c->scan_tmp, c->st, c->lc);
+  compact_run(w, c->d_segs.p, nseg, c->w_flags.p, c->w_pos.p, c->scan_tmp, c->d_dst.p, c->d_counts.p, c->st, c->lc);
+  GLIO_CUDA_TRY(cudaMemcpyAsync(c->h_counts.p, c->d_counts.p, nseg * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  if (c->prm.keep_debug) {
+    for (int s = 0; s < nseg; ++s) {
+      Slot& sl = c->slot(ids[s]);
+      const int64_t o = segs[s].offset, q = sl.Q;
+      sl.dbg_status.reserve(q); sl.dbg_idx5.reserve(5 * q); sl.dbg_sqd5.reserve(5 * q); sl.dbg_pm.reserve(q); sl.dbg_plane.reserve(4 * q);
+      GLIO_CUDA_TRY(cudaMemcpyAsync(sl.dbg_status.p, w.status + o, q, cudaMemcpyDeviceToDevice, c->st));
+      GLIO_CUDA_TRY(cudaMemcpyAsync(sl.dbg_idx5.p, w.idx5 + 5 * o, 5 * q * sizeof(int32_t), cudaMemcpyDeviceToDevice, c->st));
+      GLIO_CUDA_TRY(cudaMemcpyAsync(sl.dbg_sqd5.p, w.sqd5 + 5 * o, 5 * q * sizeof(float), cudaMemcpyDeviceToDevice, c->st));
+      GLIO_CUDA_TRY(cudaMemcpyAsync(sl.dbg_pm.p, w.pm + o, q * sizeof(float4), cudaMemcpyDeviceToDevice, c->st));
+      GLIO_CUDA_TRY(cudaMemcpyAsync(sl.dbg_plane.p, w.plane + 4 * o, 4 * q * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+      sl.dbg_Q = q;
+    }
+  }
+  GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+  for (int s = 0; s < nseg; ++s) {
+    Slot& sl = c->slot(ids[s]);
+    sl.n_match = c->h_counts.p[s];
+    if (n_match) n_match[s] = sl.n_match;
+  }
+  c->items_dirty = true;
+}
+
+void build_items(glio_ctx* c, int W) {
+  if (!c->items_dirty && c->items_W == W) return;
+  std::vector<EvalItem> items;
+  std::vector<int> start(W + 1, 0);
+  for (int k = 0; k < W; ++k) {
+    start[k] = (int)items.size();
+    if ((size_t)k >= c->slots.size() || !c->slots[k]) continue;
+    Slot& sl = *c->slots[k];
+    const bool sel = sl.n_sel >= 0;
+    const int64_t n = sel ? sl.n_sel : sl.n_match;
+    const float4* cpw = sel ? sl.s_cpw.p : sl.m_cpw.p;
+    const float4* nsd = sel ? sl.s_nsd.p : sl.m_nsd.p;
+    for (int64_t o = 0; o < n; o += GLIO_ITEM_MAX) {
+      EvalItem it; it.cpw = cpw + o; it.nsd = nsd + o; it.count = (int32_t)std::min<int64_t>(GLIO_ITEM_MAX, n - o); it.kf = k;
+      items.push_back(it);
+    }
+  }
+  start[W] = (int)items.size();
+  c->n_items = (int)items.size();
+  c->d_items.reserve(items.size() + 1); c->d_kf_item_start.reserve(W + 1);
+  c->d_partials.reserve((items.size() + 1) * GLIO_NACC);
+  c->d_out.reserve((size_t)W * GLIO_NACC); c->h_out.reserve((size_t)W * GLIO_NACC);
+  c->d_poses.reserve((size_t)W * 7); c->h_poses.reserve((size_t)W * 7);
+  if (!c->d_ticket.p) { c->d_ticket.reserve(1); GLIO_CUDA_TRY(cudaMemsetAsync(c->d_ticket.p, 0, sizeof(unsigned int), c->st)); }
+  if (!items.empty())
+    GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_items.p, items.data(), items.size() * sizeof(EvalItem), cudaMemcpyHostToDevice, c->st));
+  GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_kf_item_start.p, start.data(), (W + 1) * sizeof(int), cudaMemcpyHostToDevice, c->st));
+  GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));   // items/start are stack vectors
+  c->items_dirty = false;
+  c->items_W = W;
+}
+
+EvalParams eval_params(const glio_ctx* c) {
+  EvalParams ep;
+  for (int k = 0; k < 4; ++k) ep.q_lb[k] = c->prm.q_lb[k];
+  for (int k = 0; k < 3; ++k) ep.t_lb[k] = c->prm.t_lb[k];
+  ep.lidar_const = c->prm.lidar_const;
+  ep.huber_delta = c->prm.huber_delta;
+  return ep;
+}
+
+}  // namespace
+
+extern "C" {
+
+void glio_default_params(glio_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  p->kd_max_radius = 1.5; p->surf_dist_thres = 0.18; p->lidar_const = 7.5; p->weight_min = 0.3; p->huber_delta = 1.0;
+  p->q_lb[0] = 1.0; p->t_lb[2] = 0.28;          // GLIO/config/config_urban_hk.yaml:90-97
+  p->batch_max_radius = 1.5; p->batch_dist_thres = 0.18; p->batch_score = 2.5;
+  p->cell_size = 0.f; p->keep_debug = 0;
+}
+
+int glio_create(int device, const glio_params* params, glio_ctx** out) {
+  if (!out) return GLIO_ERR_ARG;
+  *out = nullptr;
+  glio_ctx* c = nullptr;
+  int rc = guarded(nullptr, [&] {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) throw Error{GLIO_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (glio_b200 has no CPU fallback)"};
+    GLIO_REQUIRE(device >= 0 && device < ndev, GLIO_ERR_ARG, "device index out of range");
+    GLIO_CUDA_TRY(cudaSetDevice(device));
+    c = new glio_ctx();
+    c->device = device;
+    if (params) c->prm = *params; else glio_default_params(&c->prm);
+    GLIO_CUDA_TRY(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  });
+  if (rc != GLIO_OK) { delete c; return rc; }
+  *out = c;
+  return GLIO_OK;
+}
+
+void glio_destroy(glio_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->st) cudaStreamSynchronize(c->st);
+  c->map.release(); c->map_stage.release();
+  for (auto& s : c->slots) if (s) s->release();
+  c->w_pm.release(); c->w_nsd.release(); c->w_seg.release(); c->w_order.release(); c->w_status.release(); c->w_weight.release();
+  c->w_nc.release(); c->w_plane.release(); c->w_idx5.release(); c->w_sqd5.release(); c->w_flags.release(); c->w_pos.release();
+  c->cell_count.release(); c->cell_pos.release(); c->scan_tmp.release(); c->d_segs.release(); c->d_dst.release(); c->d_counts.release();
+  c->h_counts.release(); c->d_bad.release(); c->d_keep.release(); c->d_items.release(); c->d_kf_item_start.release();
+  c->d_partials.release(); c->d_out.release(); c->d_poses.release(); c->d_r.release(); c->d_J.release(); c->h_out.release();
+  c->h_poses.release(); c->d_ticket.release();
+  if (c->st) cudaStreamDestroy(c->st);
+  delete c;
+}
+
+const char* glio_last_error(const glio_ctx* c) { return c ? c->err.c_str() : global_error(); }
+
+int glio_synchronize(glio_ctx* c) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] { GLIO_CUDA_TRY(cudaStreamSynchronize(c->st)); });
+}
+void* glio_stream(glio_ctx* c) { return c ? (void*)c->st : nullptr; }
+int64_t glio_launch_count(const glio_ctx* c) { return c ? c->lc.n : 0; }
+
+void glio_lidar_pose(const glio_params* prm, const double pose_body[7], double t2[3], double q2[4]) {
+  lidar_pose_in_map(prm->q_lb, prm->t_lb, pose_body, t2, q2);
+}
+
+int glio_set_map(glio_ctx* c, const float* xyz, int64_t M, int stride, int mem) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(M >= 5, GLIO_ERR_ARG, "map needs at least 5 points");
+    const float* d = stage_points(c, c->map_stage, xyz, M, stride, mem);
+    grid_build(c->map, d, stride, M, nullptr, nullptr, c->prm.cell_size, 3.0f, c->st, c->lc);
+    c->has_map = true;
+  });
+}
+
+int glio_assoc_scan_to_map(glio_ctx* c, int slot, const float* scan_xyz, int64_t Q, int stride, int mem,
+                           const double t[3], const double q[4], int64_t* n_match) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(t && q, GLIO_ERR_ARG, "null pose");
+    Slot& sl = c->slot(slot);
+    sl.scan_ptr = stage_points(c, sl.scan, scan_xyz, Q, stride, mem);
+    sl.Q = Q; sl.stride = stride;
+    std::vector<std::array<double, 7>> lp(1);
+    for (int k = 0; k < 3; ++k) lp[0][k] = t[k];
+    for (int k = 0; k < 4; ++k) lp[0][3 + k] = q[k];
+    associate_slots(c, std::vector<int>{slot}, lp, n_match);
+  });
+}
+
+int glio_window_set_scans(glio_ctx* c, int W, const float* const* scans, const int64_t* Q, int stride, int mem) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(W > 0 && scans && Q, GLIO_ERR_ARG, "bad window arguments");
+    for (int k = 0; k < W; ++k) {
+      Slot& sl = c->slot(k);
+      sl.scan_ptr = stage_points(c, sl.scan, scans[k], Q[k], stride, mem);
+      sl.Q = Q[k]; sl.stride = stride; sl.n_match = 0; sl.n_sel = -1;
+    }
+    c->items_dirty = true;
+  });
+}
+
+int glio_window_associate(glio_ctx* c, int W, const double* poses_body, int64_t* n_match) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(W > 0 && poses_body, GLIO_ERR_ARG, "bad window arguments");
+    std::vector<int> ids(W);
+    std::vector<std::array<double, 7>> lp(W);
+    for (int k = 0; k < W; ++k) {
+      ids[k] = k;
+      lidar_pose_in_map(c->prm.q_lb, c->prm.t_lb, poses_body + 7 * k, &lp[k][0], &lp[k][3]);   // Estimator.cpp:2216-2217
+    }
+    associate_slots(c, ids, lp, n_match);
+  });
+}
+
+int glio_get_matches(glio_ctx* c, int slot, int64_t capacity, float* cp, float* nsd, float* weight, int32_t* src, int64_t* n_out) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    Slot& sl = c->slot(slot);
+    const int64_t n = sl.n_match;
+    if (n_out) *n_out = n;
+    GLIO_REQUIRE(capacity >= n, GLIO_ERR_ARG, "capacity smaller than the match count");
+    if (n == 0) return;
+    std::vector<float4> h(n);
+    if (cp || weight) {
+      GLIO_CUDA_TRY(cudaMemcpyAsync(h.data(), sl.m_cpw.p, n * sizeof(float4), cudaMemcpyDeviceToHost, c->st));
+      GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+      for (int64_t i = 0; i < n; ++i) {
+        if (cp) { cp[3 * i] = h[i].x; cp[3 * i + 1] = h[i].y; cp[3 * i + 2] = h[i].z; }
+        if (weight) weight[i] = h[i].w;
+      }
+    }
+    if (nsd) {
+      GLIO_CUDA_TRY(cudaMemcpyAsync(nsd, sl.m_nsd.p, n * sizeof(float4), cudaMemcpyDeviceToHost, c->st));
+      GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    }
+    if (src) {
+      GLIO_CUDA_TRY(cudaMemcpyAsync(src, sl.m_src.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+      GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    }
+  });
+}
+
+int glio_get_assoc_debug(glio_ctx* c, int slot, int64_t Q, uint8_t* status, int32_t* idx5, float* sqd5, float* pm, double* plane) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(c->prm.keep_debug, GLIO_ERR_STATE, "context was created without keep_debug");
+    Slot& sl = c->slot(slot);
+    GLIO_REQUIRE(sl.dbg_Q == Q && Q > 0, GLIO_ERR_ARG, "Q does not match the slot's last association");
+    if (status) GLIO_CUDA_TRY(cudaMemcpyAsync(status, sl.dbg_status.p, Q, cudaMemcpyDeviceToHost, c->st));
+    if (idx5) GLIO_CUDA_TRY(cudaMemcpyAsync(idx5, sl.dbg_idx5.p, 5 * Q * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+    if (sqd5) GLIO_CUDA_TRY(cudaMemcpyAsync(sqd5, sl.dbg_sqd5.p, 5 * Q * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    if (plane) GLIO_CUDA_TRY(cudaMemcpyAsync(plane, sl.dbg_plane.p, 4 * Q * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    std::vector<float4> h;
+    if (pm) { h.resize(Q); GLIO_CUDA_TRY(cudaMemcpyAsync(h.data(), sl.dbg_pm.p, Q * sizeof(float4), cudaMemcpyDeviceToHost, c->st)); }
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    if (pm) for (int64_t i = 0; i < Q; ++i) { pm[3 * i] = h[i].x; pm[3 * i + 1] = h[i].y; pm[3 * i + 2] = h[i].z; }
+  });
+}
+
+int glio_select(glio_ctx* c, int slot, const int32_t* keep, int64_t n) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    Slot& sl = c->slot(slot);
+    c->items_dirty = true;
+    if (n < 0) { sl.n_sel = -1; return; }
+    GLIO_REQUIRE(n == 0 || keep, GLIO_ERR_ARG, "null selection list");
+    sl.n_sel = n;
+    if (n == 0) return;
+    c->d_keep.reserve(n); c->d_bad.reserve(1);
+    sl.s_cpw.reserve(n); sl.s_nsd.reserve(n);
+    GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_keep.p, keep, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->st));
+    GLIO_CUDA_TRY(cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->st));
+    gather_selection(c->d_keep.p, n, sl.n_match, sl.m_cpw.p, sl.m_nsd.p, nullptr, sl.s_cpw.p, sl.s_nsd.p, nullptr, c->d_bad.p, c->st, c->lc);
+    int bad = 0;
+    GLIO_CUDA_TRY(cudaMemcpyAsync(&bad, c->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    if (bad) { sl.n_sel = -1; throw Error{GLIO_ERR_ARG, "selection index out of range"}; }
+  });
+}
+
+int glio_eval_unary(glio_ctx* c, int W, const double* poses_body, int jac_kind, double* H, double* g, double* cost) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(W > 0 && W <= 4096 && poses_body, GLIO_ERR_ARG, "bad arguments");
+    GLIO_REQUIRE(jac_kind == 0 || jac_kind == 1, GLIO_ERR_ARG, "jac_kind must be 0 or 1");
+    build_items(c, W);
+    memcpy(c->h_poses.p, poses_body, (size_t)W * 7 * sizeof(double));
+    GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_poses.p, c->h_poses.p, (size_t)W * 7 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    const bool want_jac = (H != nullptr) || (g != nullptr);
+    eval_unary_run(c->d_items.p, c->n_items, W, c->d_poses.p, eval_params(c), jac_kind, want_jac, c->d_partials.p, c->d_out.p,
+                   c->d_kf_item_start.p, c->d_ticket.p, c->st, c->lc);
+    GLIO_CUDA_TRY(cudaMemcpyAsync(c->h_out.p, c->d_out.p, (size_t)W * GLIO_NACC * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    for (int k = 0; k < W; ++k) {
+      const double* o = c->h_out.p + (size_t)k * GLIO_NACC;
+      if (H) {
+        int idx = 0;
+        for (int p = 0; p < 6; ++p) for (int q = p; q < 6; ++q) { H[36 * k + 6 * p + q] = o[idx]; H[36 * k + 6 * q + p] = o[idx]; ++idx; }
+      }
+      if (g) for (int p = 0; p < 6; ++p) g[6 * k + p] = o[21 + p];
+      if (cost) cost[k] = o[27];
+    }
+  });
+}
+
+int glio_eval_unary_residuals(glio_ctx* c, int slot, const double pose_body[7], int jac_kind, int64_t capacity, double* r, double* J, int64_t* n_out) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    Slot& sl = c->slot(slot);
+    const bool sel = sl.n_sel >= 0;
+    const int64_t n = sel ? sl.n_sel : sl.n_match;
+    if (n_out) *n_out = n;
+    GLIO_REQUIRE(capacity >= n, GLIO_ERR_ARG, "capacity smaller than the residual count");
+    if (n == 0) return;
+    c->d_r.reserve(n); c->d_J.reserve(6 * n); c->d_poses.reserve(7); c->h_poses.reserve(7);
+    memcpy(c->h_poses.p, pose_body, 7 * sizeof(double));
+    GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_poses.p, c->h_poses.p, 7 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    eval_unary_residuals_run(sel ? sl.s_cpw.p : sl.m_cpw.p, sel ? sl.s_nsd.p : sl.m_nsd.p, n, c->d_poses.p, eval_params(c), jac_kind,
+                             c->d_r.p, c->d_J.p, c->st, c->lc);
+    if (r) GLIO_CUDA_TRY(cudaMemcpyAsync(r, c->d_r.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    if (J) GLIO_CUDA_TRY(cudaMemcpyAsync(J, c->d_J.p, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+// common.cuh — shared device/host declarations of the glio_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/glio_b200.h"
+
+namespace glio {
+
+// ----------------------------------------------------------------------------------------------
+// error plumbing: every CUDA call is checked; failures become a status + message, never abort.
+// ----------------------------------------------------------------------------------------------
+struct Error {
+  int code;
+  std::string msg;
+};
+void set_global_error(const std::string& m);
+const char* global_error();
+
+#define GLIO_CUDA_TRY(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      char _b[512];                                                                           \
+      snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      throw ::glio::Error{GLIO_ERR_CUDA, _b};                                                 \
+    }                                                                                         \
+  } while (0)
+
+#define GLIO_REQUIRE(cond, code, text)                      \
+  do {                                                      \
+    if (!(cond)) throw ::glio::Error{(code), (text)};       \
+  } while (0)
+
+// grow-only device buffer
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t n) {
+    if (n <= cap) return;
+    if (p) GLIO_CUDA_TRY(cudaFree(p));
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 64;
+    GLIO_CUDA_TRY(cudaMalloc((void**)&p, want * sizeof(T)));
+    cap = want;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <class T>
+struct PinnedBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t n) {
+    if (n <= cap) return;
+    if (p) GLIO_CUDA_TRY(cudaFreeHost(p));
+    p = nullptr; cap = 0;
+    size_t want = n + n / 8 + 64;
+    GLIO_CUDA_TRY(cudaMallocHost((void**)&p, want * sizeof(T)));
+    cap = want;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// ----------------------------------------------------------------------------------------------
+// Uniform grid over a point cloud (K0 output).  Points are counting-sorted by cell with x the
+// fastest-varying cell coordinate, so the three x-adjacent cells of a (y,z) row are ONE contiguous range.
+// pts[k] = (x, y, z, bitcast(original index)).
+// ----------------------------------------------------------------------------------------------
+struct GridDesc {
+  float ox, oy, oz;     // origin (min corner of cell (0,0,0))
+  float cell, inv_cell;
+  int nx, ny, nz;
+  int64_t npts;
+  const int* cell_start;   // [nx*ny*nz + 1]
+  const float4* pts;       // [npts] sorted by cell
+};
+
+// One association segment = one scan transformed by one pose, queried against the launch's grid.
+struct SegDesc {
+  const float* src;     // scan points, stride floats apart
+  int stride;
+  int64_t count;
+  int64_t offset;       // first global query index of the segment
+  double t[3];
+  double q[4];
+};
+
+struct AssocGates {
+  double max_radius;    // compared with the squared 5th distance (quirk Q1)
+  double dist_thres;
+  double weight_min;
+};
+
+// workspace views handed to the association kernels (global query index g in [0, Qt))
+struct AssocWork {
+  int64_t Qt;
+  float4* pm;           // transformed query (x,y,z, _)
+  uint16_t* seg;        // segment id of the query
+  uint32_t* order;      // queries sorted by grid cell
+  uint8_t* status;
+  float4* nsd;          // weight*n, weight*d   (scan-to-map)
+  float* weight;
+  double* normal_cent;  // 6 per query (pair mode) or nullptr
+  // debug (nullable)
+  int32_t* idx5;
+  float* sqd5;
+  double* plane;
+};
+
+// destination of one segment's compacted matches
+struct CompactDst {
+  float4* cpw;
+  float4* nsd;
+  double* nc;
+  int32_t* src;
+};
+
+// per-block work item of the evaluation kernels: a contiguous run of residuals of one keyframe
+struct EvalItem {
+  const float4* cpw;    // (cp.xyz, weight)
+  const float4* nsd;    // (n_s.xyz, d_s)
+  int32_t count;
+  int32_t kf;
+};
+
+struct LaunchCounter { int64_t n = 0; };
+
+// ---- K0 (grid.cu)
+struct GridBuild {
+  DevBuf<int> cell_start;
+  DevBuf<float4> pts;
+  DevBuf<float4> tmp4;     // unsorted (transformed) points, original order: (x,y,z,idx)
+  DevBuf<int> fill;        // scatter cursors
+  DevBuf<int> scan_tmp;
+  DevBuf<int> bounds;      // 6 order-preserving ints on device
+  GridDesc desc{};
+  void release() { cell_start.release(); pts.release(); tmp4.release(); fill.release(); scan_tmp.release(); bounds.release(); }
+};
+void grid_build(GridBuild& gb, const float* d_xyz, int stride, int64_t n, const double* t, const double* q,
+                float cell_size_hint, float pts_per_cell, cudaStream_t st, LaunchCounter& lc);
+void exclusive_scan_i32(const int* in, int* out, int64_t n, DevBuf<int>& tmp, cudaStream_t st, LaunchCounter& lc);
+
+// ---- K1 / K1b (assoc.cu)
+void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const AssocWork& w, const AssocGates& gates,
+               const float* oth_local, int oth_stride, DevBuf<int>& cell_count, DevBuf<int>& cell_pos,
+               DevBuf<int>& scan_tmp, cudaStream_t st, LaunchCounter& lc);
+void compact_run(const AssocWork& w, const SegDesc* d_segs, int nseg, int* d_flags, int* d_pos, DevBuf<int>& scan_tmp,
+                 const void* d_dst /*CompactDst[nseg]*/, int* d_counts, cudaStream_t st, LaunchCounter& lc);
+void gather_selection(const int32_t* d_keep, int64_t n, int64_t n_match, const float4* cpw, const float4* nsd, const double* nc,
+                      float4* o_cpw, float4* o_nsd, double* o_nc, int* d_bad, cudaStream_t st, LaunchCounter& lc);
+
+// ---- K2 / K2b / K2e (eval.cu)
+struct EvalParams {
+  double q_lb[4], t_lb[3];
+  double lidar_const;
+  double huber_delta;
+};
+constexpr int GLIO_NACC = 28;        // 21 upper-triangular H + 6 g + 1 cost
+constexpr int GLIO_ITEM_MAX = 2048;  // residuals per evaluation work item
+void eval_unary_run(const EvalItem* d_items, int nitems, int W, const double* d_poses, const EvalParams& ep, int jac_kind,
+                    bool want_jac, double* d_partials, double* d_out, const int* d_kf_item_start, unsigned int* d_ticket,
+                    cudaStream_t st, LaunchCounter& lc);
+void eval_unary_residuals_run(const float4* cpw, const float4* nsd, int64_t n, const double* d_pose, const EvalParams& ep,
+                              int jac_kind, double* d_r, double* d_J, cudaStream_t st, LaunchCounter& lc);
+
+}  // namespace glio

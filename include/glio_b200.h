@@ -1,0 +1,158 @@
+/*
+ * glio_b200.h — C ABI of the B200-native LiDAR hot path of GLIO.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / Eigen / PCL / Ceres / ROS types.
+ * Every entry point names the reference interface it replaces (paths relative to the GLIO repository
+ * root, reference commit 332d19ff).  The Ceres-compatible C++ shim (glio_b200/shim/ceres/ headers) and the
+ * Python mirror (glio_b200/api.py) are thin layers over exactly these functions.
+ *
+ * Conventions
+ *   - points: float32 xyz with a caller-given stride in floats (3 = packed xyz, 8 = pcl::PointXYZI as
+ *     stored in pcl::PointCloud<PointType>::points, GLIO/include/utils/common.h:87-89).
+ *   - poses: double[7] = t(x,y,z), q(w,x,y,z) — the reference's tmpTrans[k] / tmpQuat[k] parameter
+ *     blocks (GLIO/src/Estimator.cpp:345-347).
+ *   - every function returns 0 on success or a negative glio_status; glio_last_error() gives the text.
+ *     No exception crosses the boundary and nothing aborts.
+ *   - mem: GLIO_HOST pointers are copied for the duration of the call only; GLIO_DEVICE pointers are
+ *     device addresses on the context's GPU (used by bench "value" runs with inputs resident in HBM).
+ *   - a glio_ctx is single-threaded; create one per concurrent caller (window solve / batch solve run on
+ *     different threads in the reference, Estimator.cpp:5352-5368).  Each context owns one CUDA stream.
+ *   - there is NO CPU fallback: without a CUDA device glio_create fails with GLIO_ERR_NO_DEVICE.
+ */
+#ifndef GLIO_B200_H
+#define GLIO_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct glio_ctx glio_ctx;
+
+typedef enum {
+  GLIO_OK = 0,
+  GLIO_ERR_NO_DEVICE = -1,
+  GLIO_ERR_CUDA = -2,
+  GLIO_ERR_ARG = -3,
+  GLIO_ERR_STATE = -4,
+  GLIO_ERR_NCCL = -5,
+  GLIO_ERR_NUMERIC = -6
+} glio_status;
+
+enum { GLIO_HOST = 0, GLIO_DEVICE = 1 };
+
+/* per-query association status (mirrors the reference's three failure counters, Estimator.cpp:3641-3643) */
+enum { GLIO_MATCH_VALID = 0, GLIO_MATCH_FAIL_RADIUS = 1, GLIO_MATCH_FAIL_PLANE = 2, GLIO_MATCH_FAIL_WEIGHT = 3 };
+
+/* All tunables of the path in one POD (SURVEY.md §5 "Config / flags"). */
+typedef struct {
+  double kd_max_radius;    /* Estimator/kd_max_radius 1.5 — compared with a SQUARED distance (Estimator.cpp:3651) */
+  double surf_dist_thres;  /* Estimator/surf_dist_thres 0.18 (Estimator.cpp:3671) */
+  double lidar_const;      /* Estimator/lidar_const 7.5 (Estimator.cpp:3690) */
+  double weight_min;       /* 0.3 hard-coded (Estimator.cpp:3681) */
+  double huber_delta;      /* lossKernel 1.0 (Estimator.cpp:70,2092); <= 0 disables the loss */
+  double q_lb[4];          /* extrinsic, wxyz (Estimator.cpp:270-274,873-877) */
+  double t_lb[3];
+  double batch_max_radius; /* 1.5 hard-coded (Estimator.cpp:3751) */
+  double batch_dist_thres; /* 0.18 hard-coded (Estimator.cpp:3778) */
+  double batch_score;      /* 2.5 hard-coded (Estimator.cpp:3798) */
+  float cell_size;         /* uniform-grid cell edge in metres; 0 = choose from point density */
+  int32_t keep_debug;      /* 1: keep idx5/sqd5/plane/pm per query for glio_get_assoc_debug (parity tests) */
+} glio_params;
+
+void glio_default_params(glio_params* p);
+
+/* lifecycle */
+int glio_create(int device, const glio_params* params, glio_ctx** out);
+void glio_destroy(glio_ctx* ctx);
+const char* glio_last_error(const glio_ctx* ctx);   /* ctx may be NULL: last global error */
+int glio_synchronize(glio_ctx* ctx);
+/* the context's CUDA stream (cudaStream_t as void*) so callers can time with events on it */
+void* glio_stream(glio_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py "gpu_launches") */
+int64_t glio_launch_count(const glio_ctx* ctx);
+
+/* lidar->map pose of a keyframe:  Q2 = Q * q_lb^-1 ; T2 = T - Q2 * t_lb   (Estimator.cpp:2216-2217) */
+void glio_lidar_pose(const glio_params* prm, const double pose_body[7], double t2[3], double q2[4]);
+
+/* ---- K0: local-map upload + uniform-grid build.
+ * Replaces kd_tree_surf_local_map->setInputCloud(surf_local_map_ds)  (Estimator.cpp:2056). */
+int glio_set_map(glio_ctx* ctx, const float* xyz, int64_t M, int stride_floats, int mem);
+
+/* ---- K1: scan-to-map surf association for ONE keyframe slot.
+ * Replaces Estimator::findCorrespondingSurfFeatures(idx, q, t)  (Estimator.cpp:3633-3708):
+ * q,t is the lidar->map pose (Q2,T2 of Estimator.cpp:2216-2217).  The scan stays resident in the slot.
+ * *n_match receives vec_surf_res_cnt[idVec].  Matches are kept on the device in scan order (the order of the
+ * reference's push_back), as (point, weight*normal, weight*d, weight). */
+int glio_assoc_scan_to_map(glio_ctx* ctx, int slot, const float* scan_xyz, int64_t Q, int stride_floats, int mem,
+                           const double t[3], const double q[4], int64_t* n_match);
+
+/* All W keyframes of the window in one launch (same results as W calls of glio_assoc_scan_to_map).
+ * poses_body[W*7] are the keyframe (IMU-body) poses tmpTrans/tmpQuat; the lidar->map pose is formed on the
+ * device-side host code exactly as Estimator.cpp:2216-2217 with params.q_lb/t_lb. */
+int glio_window_set_scans(glio_ctx* ctx, int W, const float* const* scans, const int64_t* Q, int stride_floats, int mem);
+int glio_window_associate(glio_ctx* ctx, int W, const double* poses_body, int64_t* n_match /*W*/);
+
+/* copy-out of one slot's matches (parity tests, and the Ceres shim's host view).  Any pointer may be NULL.
+ *   cp[3n] float (scan-frame point), nsd[4n] float (weight*n, weight*d), weight[n] float, src[n] int32
+ *   (index of the match's scan point).  score = lidar_const * (double)weight. */
+int glio_get_matches(glio_ctx* ctx, int slot, int64_t capacity, float* cp, float* nsd, float* weight, int32_t* src,
+                     int64_t* n_match);
+/* per-query debug view (needs params.keep_debug): status[Q] u8, idx5[5Q], sqd5[5Q], pm[3Q], plane[4Q] double */
+int glio_get_assoc_debug(glio_ctx* ctx, int slot, int64_t Q, uint8_t* status, int32_t* idx5, float* sqd5, float* pm,
+                         double* plane);
+
+/* ---- feature selection as an INPUT (Estimator.cpp:3894-3992 is an RNG sub-sampling).
+ * keep[n] are indices into the slot's match list; n < 0 clears the selection (all matches active). */
+int glio_select(glio_ctx* ctx, int slot, const int32_t* keep, int64_t n);
+
+/* ---- K2: evaluate all active unary plane residuals at the given body poses.
+ * Replaces ceres::ResidualBlock::Evaluate over LidarPlaneNormFactor (LidarKeyframeFactor.h:73-122) + HuberLoss +
+ * QuaternionParameterization and the J^T J / J^T r accumulation for those blocks.
+ *   jac_kind 0: Ceres tangent Jacobian (solve path); 1: ambient x,y,z quaternion columns
+ *   (marginalisation path, MarginalizationFactor.cpp:9-17).
+ *   H[W*36] row-major 6x6 per keyframe (t | rotation), g[W*6] = J^T r, cost[W] = sum 0.5*rho(r^2).
+ *   H and g may be NULL (cost-only evaluation at a candidate point). */
+int glio_eval_unary(glio_ctx* ctx, int W, const double* poses_body, int jac_kind, double* H, double* g, double* cost);
+
+/* per-residual view for the Ceres-API path: r[n], J[6n] (corrected, tangent) for one slot */
+int glio_eval_unary_residuals(glio_ctx* ctx, int slot, const double pose_body[7], int jac_kind, int64_t capacity,
+                              double* r, double* J, int64_t* n);
+
+/* ---- K1b: scan-to-multiscan (batch) association.
+ * Replaces findGlobalCorrespondingSurfFeatures_Batch / ...Add_Batch (Estimator.cpp:3710-3892).
+ * Frames are registered once; a pair (cur, oth) associates every point of frame cur against frame oth. */
+int glio_batch_set_frame(glio_ctx* ctx, int frame, const float* scan_xyz, int64_t Q, int stride_floats, int mem,
+                         const double pose[7]);
+/* associate `cur` against each of oth[n_oth]; n_match[n_oth] receives gl_vec_surf_res_cnt[cur][oth]. */
+int glio_batch_associate(glio_ctx* ctx, int cur, const int32_t* oth, int n_oth, int64_t* n_match);
+/* all pairs at once: pairs_cur[n], pairs_oth[n] */
+int glio_batch_associate_pairs(glio_ctx* ctx, const int32_t* pairs_cur, const int32_t* pairs_oth, int64_t n_pairs,
+                               int64_t* n_match);
+int glio_batch_get_matches(glio_ctx* ctx, int cur, int oth, int64_t capacity, float* cp, float* weight,
+                           double* normal_cent /*6n*/, int32_t* src, int64_t* n_match);
+int glio_batch_select(glio_ctx* ctx, int cur, int oth, const int32_t* keep, int64_t n);
+int glio_batch_clear(glio_ctx* ctx);
+
+/* ---- K2b: evaluate all active binary plane residuals.
+ * Replaces ResidualBlock::Evaluate over BinaryLidarPlaneNormFactor (LidarKeyframeFactor.h:124-164).
+ *   poses[K*7]; outputs in block-banded form: Hdiag[K*36], Hoff[n_pairs*36] (block (cur,oth), row = cur
+ *   tangent, col = oth tangent, in the order pairs were associated; query with glio_batch_pair_list),
+ *   g[K*6], cost (scalar). */
+int glio_eval_binary(glio_ctx* ctx, int K, const double* poses, double* Hdiag, double* Hoff, double* g, double* cost);
+int glio_batch_pair_list(glio_ctx* ctx, int64_t capacity, int32_t* cur, int32_t* oth, int64_t* n_pairs);
+
+/* ---- K2e: edge residuals (LidarEdgeFactor, LidarKeyframeFactor.h:12-70 — defined but never instantiated
+ * by the reference; evaluated here from caller-provided correspondences). */
+int glio_set_edges(glio_ctx* ctx, int slot, const float* cp, const float* pa, const float* pb, const double* s,
+                   int64_t n, int mem);
+int glio_eval_edge(glio_ctx* ctx, int W, const double* poses_body, double* H, double* g, double* cost);
+
+/* ---- multi-GPU (batch path only): sum the block buffers over ranks with NCCL (SURVEY §8 e).
+ * comm is an ncclComm_t as void*. */
+int glio_allreduce_blocks(glio_ctx* ctx, void* nccl_comm, double* d_buf, int64_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

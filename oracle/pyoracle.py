@@ -1,0 +1,193 @@
+"""ctypes binding of the CPU oracle (oracle/libglio_oracle.so).
+
+TEST INFRASTRUCTURE ONLY — imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Nothing under glio_b200/ may import this module.
+PARITY UNPINNED: see oracle/glio_oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+GO_VALID, GO_FAIL_RADIUS, GO_FAIL_PLANE, GO_FAIL_WEIGHT = 0, 1, 2, 3
+
+
+class AssocParams(C.Structure):
+    _fields_ = [("kd_max_radius", C.c_double), ("surf_dist_thres", C.c_double),
+                ("lidar_const", C.c_double), ("weight_min", C.c_double),
+                ("batch_max_radius", C.c_double), ("batch_dist_thres", C.c_double),
+                ("batch_score", C.c_double)]
+
+
+def default_params():
+    # GLIO/config/config_urban_hk.yaml:70-72, Estimator.cpp:3681,3751,3778,3798
+    return AssocParams(1.5, 0.18, 7.5, 0.3, 1.5, 0.18, 2.5)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libglio_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libglio_oracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = C.CDLL(so)
+        _LIB.go_kdtree_build.restype = C.c_void_p
+        _LIB.go_assoc_scan_to_map.restype = C.c_int64
+        _LIB.go_assoc_pair.restype = C.c_int64
+        _LIB.go_plane_solve5.restype = C.c_int
+        if hasattr(_LIB, "go_solver_create"):
+            _LIB.go_solver_create.restype = C.c_void_p
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def transform_points(xyz, t, q):
+    xyz = _f32(xyz).reshape(-1, 3)
+    out = np.empty_like(xyz)
+    t = _f64(t); q = _f64(q)
+    lib().go_transform_points(_p(xyz), C.c_int64(len(xyz)), _p(t), _p(q), _p(out))
+    return out
+
+
+def knn5_brute(map_xyz, qry_xyz):
+    m = _f32(map_xyz).reshape(-1, 3); q = _f32(qry_xyz).reshape(-1, 3)
+    idx = np.empty((len(q), 5), np.int32); sqd = np.empty((len(q), 5), np.float32)
+    tie = np.empty(len(q), np.uint8)
+    lib().go_knn5_brute(_p(m), C.c_int64(len(m)), _p(q), C.c_int64(len(q)), _p(idx), _p(sqd), _p(tie))
+    return idx, sqd, tie
+
+
+class KdTree:
+    def __init__(self, xyz):
+        self.xyz = _f32(xyz).reshape(-1, 3)
+        self.h = C.c_void_p(lib().go_kdtree_build(_p(self.xyz), C.c_int64(len(self.xyz))))
+
+    def knn5(self, qry):
+        q = _f32(qry).reshape(-1, 3)
+        idx = np.empty((len(q), 5), np.int32); sqd = np.empty((len(q), 5), np.float32)
+        lib().go_kdtree_knn5(self.h, _p(q), C.c_int64(len(q)), _p(idx), _p(sqd))
+        return idx, sqd
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().go_kdtree_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def plane_solve5(A):
+    A = _f64(A).reshape(5, 3)
+    x = np.zeros(3)
+    npiv = lib().go_plane_solve5(_p(A), _p(x))
+    return x, npiv
+
+
+def assoc_scan_to_map(map_xyz, scan_xyz, t, q, prm=None, tree=None, nthreads=0):
+    prm = prm or default_params()
+    m = _f32(map_xyz).reshape(-1, 3); s = _f32(scan_xyz).reshape(-1, 3)
+    Q = len(s)
+    out = dict(status=np.empty(Q, np.uint8), idx5=np.empty((Q, 5), np.int32), sqd5=np.empty((Q, 5), np.float32),
+               pm=np.empty((Q, 3), np.float32), plane=np.empty((Q, 4), np.float64),
+               nsd=np.empty((Q, 4), np.float32), weight=np.empty(Q, np.float32), score=np.empty(Q, np.float64))
+    t = _f64(t); q = _f64(q)
+    n = lib().go_assoc_scan_to_map(C.byref(prm), _p(m), C.c_int64(len(m)), tree.h if tree is not None else None,
+                                   _p(s), C.c_int64(Q), _p(t), _p(q), _p(out["status"]), _p(out["idx5"]),
+                                   _p(out["sqd5"]), _p(out["pm"]), _p(out["plane"]), _p(out["nsd"]),
+                                   _p(out["weight"]), _p(out["score"]), C.c_int(nthreads))
+    out["nvalid"] = int(n)
+    return out
+
+
+def assoc_pair(cur_xyz, t_c, q_c, oth_xyz, t_o, q_o, prm=None, use_kdtree=True, nthreads=0):
+    prm = prm or default_params()
+    c = _f32(cur_xyz).reshape(-1, 3); o = _f32(oth_xyz).reshape(-1, 3)
+    Q = len(c)
+    out = dict(status=np.empty(Q, np.uint8), idx5=np.empty((Q, 5), np.int32), sqd5=np.empty((Q, 5), np.float32),
+               weight=np.empty(Q, np.float32), score=np.empty(Q, np.float64), normal_cent=np.empty((Q, 6), np.float64))
+    n = lib().go_assoc_pair(C.byref(prm), _p(c), C.c_int64(Q), _p(_f64(t_c)), _p(_f64(q_c)), _p(o),
+                            C.c_int64(len(o)), _p(_f64(t_o)), _p(_f64(q_o)), C.c_int(1 if use_kdtree else 0),
+                            _p(out["status"]), _p(out["idx5"]), _p(out["sqd5"]), _p(out["weight"]),
+                            _p(out["score"]), _p(out["normal_cent"]), C.c_int(nthreads))
+    out["nvalid"] = int(n)
+    return out
+
+
+def eval_unary(poses, q_lb, t_lb, kf, cp, nsd, score, huber_delta=1.0, mode=0, jac_kind=0, per_residual=True):
+    poses = _f64(poses).reshape(-1, 7); W = len(poses)
+    kf = np.ascontiguousarray(kf, np.int32); cp = _f32(cp).reshape(-1, 3); nsd = _f32(nsd).reshape(-1, 4)
+    score = _f64(score); N = len(kf)
+    r = np.empty(N) if per_residual else None
+    J = np.empty((N, 6)) if per_residual else None
+    c = np.empty(N) if per_residual else None
+    H = np.zeros((6 * W, 6 * W)); g = np.zeros(6 * W); ct = np.zeros(1)
+    lib().go_eval_unary(C.c_int(mode), C.c_int(jac_kind), C.c_int(W), _p(poses), _p(_f64(q_lb)), _p(_f64(t_lb)),
+                        C.c_double(huber_delta), C.c_int64(N), _p(kf), _p(cp), _p(nsd), _p(score),
+                        _p(r), _p(J), _p(c), _p(H), _p(g), _p(ct))
+    return dict(r=r, J=J, cost=c, H=H, g=g, cost_total=float(ct[0]))
+
+
+def eval_binary(poses, kf_c, kf_o, cp, normal_cent, score, huber_delta=0.0, mode=0, per_residual=True):
+    poses = _f64(poses).reshape(-1, 7); K = len(poses)
+    kf_c = np.ascontiguousarray(kf_c, np.int32); kf_o = np.ascontiguousarray(kf_o, np.int32)
+    cp = _f32(cp).reshape(-1, 3); nc = _f64(normal_cent).reshape(-1, 6); score = _f64(score); N = len(kf_c)
+    r = np.empty(N) if per_residual else None
+    J = np.empty((N, 12)) if per_residual else None
+    c = np.empty(N) if per_residual else None
+    H = np.zeros((6 * K, 6 * K)); g = np.zeros(6 * K); ct = np.zeros(1)
+    lib().go_eval_binary(C.c_int(mode), C.c_int(K), _p(poses), C.c_double(huber_delta), C.c_int64(N), _p(kf_c),
+                         _p(kf_o), _p(cp), _p(nc), _p(score), _p(r), _p(J), _p(c), _p(H), _p(g), _p(ct))
+    return dict(r=r, J=J, cost=c, H=H, g=g, cost_total=float(ct[0]))
+
+
+def eval_edge(poses, q_lb, t_lb, kf, cp, pa, pb, s, huber_delta=1.0, mode=0, per_residual=True):
+    poses = _f64(poses).reshape(-1, 7); W = len(poses)
+    kf = np.ascontiguousarray(kf, np.int32); cp = _f32(cp).reshape(-1, 3)
+    pa = _f32(pa).reshape(-1, 3); pb = _f32(pb).reshape(-1, 3); s = _f64(s); N = len(kf)
+    r = np.empty(N) if per_residual else None
+    J = np.empty((N, 6)) if per_residual else None
+    c = np.empty(N) if per_residual else None
+    H = np.zeros((6 * W, 6 * W)); g = np.zeros(6 * W); ct = np.zeros(1)
+    lib().go_eval_edge(C.c_int(mode), C.c_int(W), _p(poses), _p(_f64(q_lb)), _p(_f64(t_lb)), C.c_double(huber_delta),
+                       C.c_int64(N), _p(kf), _p(cp), _p(pa), _p(pb), _p(s), _p(r), _p(J), _p(c), _p(H), _p(g), _p(ct))
+    return dict(r=r, J=J, cost=c, H=H, g=g, cost_total=float(ct[0]))
+
+
+def huber(a, s):
+    rho = np.zeros(3); lib().go_huber(C.c_double(a), C.c_double(s), _p(rho)); return rho
+
+
+def corrector(sq_norm, rho):
+    out = np.zeros(3); lib().go_corrector(C.c_double(sq_norm), _p(_f64(rho)), _p(out)); return out
+
+
+def quat_plus(x, delta):
+    out = np.zeros(4); lib().go_quat_plus(_p(_f64(x)), _p(_f64(delta)), _p(out)); return out
+
+
+def quat_plus_jacobian(x):
+    out = np.zeros(12); lib().go_quat_plus_jacobian(_p(_f64(x)), _p(out)); return out.reshape(4, 3)

@@ -1,0 +1,59 @@
+"""K0+K1 parity: CUDA scan-to-map association vs the CPU oracle, through the C ABI (bit-exact bar)."""
+import numpy as np
+import pytest
+
+from glio_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from glio_b200 import api
+    c = api.Context(0, keep_debug=1)
+    yield c
+    c.close()
+
+
+def _check_slot(ctx, oracle, P, k, t2, q2, tree):
+    o = oracle.assoc_scan_to_map(P["map_xyz"], P["scans"][k], t2, q2, tree=tree)
+    Q = len(P["scans"][k])
+    d = ctx.get_assoc_debug(k, Q)
+    assert np.array_equal(d["pm"], o["pm"]), "transformed query points differ"
+    assert np.array_equal(d["status"], o["status"]), f"status mismatch at {np.nonzero(d['status'] != o['status'])[0][:10]}"
+    ok = o["status"] != oracle.GO_FAIL_RADIUS
+    assert np.array_equal(d["idx5"][ok], o["idx5"][ok]), "kNN indices differ"
+    assert np.array_equal(d["sqd5"][ok], o["sqd5"][ok]), "kNN distances differ"
+    assert np.array_equal(d["plane"][ok], o["plane"][ok]), "plane parameters differ (bit-exact expected)"
+    m = ctx.get_matches(k, Q)
+    v = o["status"] == oracle.GO_VALID
+    assert m["n"] == o["nvalid"] == int(v.sum())
+    assert np.array_equal(m["src"], np.nonzero(v)[0].astype(np.int32))
+    assert np.array_equal(m["cp"], P["scans"][k][v])
+    assert np.array_equal(m["nsd"], o["nsd"][v])
+    assert np.array_equal(m["weight"], o["weight"][v])
+    return o
+
+
+@pytest.mark.parametrize("W,Q,M,seed", [(3, 2000, 30000, 11), (5, 1000, 50000, synth.SEED0 + 1)])
+def test_scan_to_map_single_slot_calls(ctx, oracle, W, Q, M, seed):
+    P = synth.window_problem(W=W, Q=Q, M=M, seed=seed)
+    ctx.set_map(P["map_xyz"])
+    tree = oracle.KdTree(P["map_xyz"])
+    for k in range(W):
+        t2, q2 = ctx.lidar_pose(P["poses_init"][k])
+        n = ctx.assoc_scan_to_map(k, P["scans"][k], t2, q2)
+        o = _check_slot(ctx, oracle, P, k, t2, q2, tree)
+        assert n == o["nvalid"]
+
+
+def test_window_associate_equals_single_calls(ctx, oracle):
+    P = synth.window_problem(W=4, Q=3000, M=40000, seed=5)
+    ctx.set_map(P["map_xyz"])
+    tree = oracle.KdTree(P["map_xyz"])
+    ctx.window_set_scans(P["scans"])
+    nm = ctx.window_associate(P["poses_init"])
+    for k in range(4):
+        t2, q2 = ctx.lidar_pose(P["poses_init"][k])
+        o = _check_slot(ctx, oracle, P, k, t2, q2, tree)
+        assert nm[k] == o["nvalid"]
