@@ -203,3 +203,111 @@ class Context:
                                                       _ptr(r), _ptr(J), C.byref(n)))
         n = int(n.value)
         return r[:n], J[:n]
+
+
+# ---------------------------------------------------------------------------------------------------
+# minimizer iteration (ceres::Solve replacement for the window problem) and stand-in host factors
+# ---------------------------------------------------------------------------------------------------
+class SolverOptions(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int32), ("dogleg_type", C.c_int32), ("use_nonmonotonic_steps", C.c_int32),
+                ("max_consecutive_nonmonotonic_steps", C.c_int32), ("initial_trust_region_radius", C.c_double),
+                ("max_trust_region_radius", C.c_double), ("min_trust_region_radius", C.c_double),
+                ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
+                ("max_num_consecutive_invalid_steps", C.c_int32), ("jacobi_scaling", C.c_int32),
+                ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+                ("fuse_candidate_jacobian", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Iteration(C.Structure):
+    _fields_ = [("iteration", C.c_int32), ("step_is_valid", C.c_int32), ("step_is_successful", C.c_int32), ("reserved", C.c_int32),
+                ("cost", C.c_double), ("cost_change", C.c_double), ("gradient_max_norm", C.c_double), ("gradient_norm", C.c_double),
+                ("step_norm", C.c_double), ("relative_decrease", C.c_double), ("trust_region_radius", C.c_double), ("mu", C.c_double)]
+
+
+class SolverSummary(C.Structure):
+    _fields_ = [("termination", C.c_int32), ("num_iterations", C.c_int32), ("num_successful_steps", C.c_int32),
+                ("num_unsuccessful_steps", C.c_int32), ("num_evaluations", C.c_int32), ("num_jacobian_evaluations", C.c_int32),
+                ("num_linear_solves", C.c_int32), ("num_valid_steps", C.c_int32), ("initial_cost", C.c_double),
+                ("final_cost", C.c_double), ("message", C.c_char * 128)]
+
+
+HOST_FACTORS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,
+                              C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
+def default_solver_options(**kw):
+    o = SolverOptions()
+    lib().glio_default_solver_options(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def iterations_to_dicts(log, n):
+    names = [f[0] for f in Iteration._fields_ if f[0] != "reserved"]
+    return [{k: getattr(log[i], k) for k in names} for i in range(n)]
+
+
+class HostFactorSet:
+    """Stand-in host factors (prior / between / range) evaluated analytically on the CPU by the library."""
+
+    def __init__(self):
+        L = lib()
+        L.glio_hf_create.restype = C.c_void_p
+        L.glio_hf_destroy.argtypes = [C.c_void_p]
+        self._lib = L
+        self._h = C.c_void_p(L.glio_hf_create())
+
+    def add_prior(self, kf, t0, q0, sb0, sqrt_w):
+        a = [np.ascontiguousarray(v, np.float64) if v is not None else None for v in (t0, q0, sb0, sqrt_w)]
+        self._lib.glio_hf_add_prior(self._h, C.c_int(kf), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]))
+
+    def add_between(self, i, j, dp, dq, dv, dt, sqrt_w):
+        a = [np.ascontiguousarray(v, np.float64) for v in (dp, dq, dv, sqrt_w)]
+        self._lib.glio_hf_add_between(self._h, C.c_int(i), C.c_int(j), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), C.c_double(dt), _ptr(a[3]))
+
+    def add_range(self, kf, lever, sat, rho, w):
+        a = [np.ascontiguousarray(v, np.float64) for v in (lever, sat)]
+        self._lib.glio_hf_add_range(self._h, C.c_int(kf), _ptr(a[0]), _ptr(a[1]), C.c_double(rho), C.c_double(w))
+
+    def evaluate(self, poses, speed_bias=None, want_jac=True):
+        pb = np.ascontiguousarray(poses, np.float64).reshape(-1, 7); W = len(pb)
+        sb = None if speed_bias is None else np.ascontiguousarray(speed_bias, np.float64).reshape(W, 9)
+        n = W * (15 if sb is not None else 6)
+        H = np.zeros((n, n)); g = np.zeros(n); c = np.zeros(1)
+        rc = self._lib.glio_hf_evaluate(self._h, C.c_int(W), _ptr(pb), _ptr(sb), C.c_int(1 if want_jac else 0), _ptr(H), _ptr(g), _ptr(c))
+        assert rc == 0
+        return H, g, float(c[0])
+
+    @property
+    def callback(self):
+        return C.cast(self._lib.glio_hf_evaluate, HOST_FACTORS_FN), self._h
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.glio_hf_destroy(self._h); self._h = None
+        except Exception:
+            pass
+
+
+def _window_solve(self, poses, speed_bias=None, host_factors=None, options=None, max_log=256):
+    """ceres::Solve for the window problem (Estimator.cpp:2424-2433).  Returns dict(poses, speed_bias, summary, iterations, steps)."""
+    pb = np.array(poses, np.float64).reshape(-1, 7).copy(); W = len(pb)
+    sb = None if speed_bias is None else np.array(speed_bias, np.float64).reshape(W, 9).copy()
+    n = W * (15 if sb is not None else 6)
+    opt = options if options is not None else default_solver_options()
+    summ = SolverSummary(); log = (Iteration * max_log)(); steps = np.zeros((max_log, n))
+    if host_factors is None:
+        fn, user = C.cast(None, HOST_FACTORS_FN), None
+    elif isinstance(host_factors, HostFactorSet):
+        fn, user = host_factors.callback
+    else:
+        fn, user = host_factors, None          # a HOST_FACTORS_FN instance
+    self._chk(self._lib.glio_window_solve(self._h, C.c_int(W), _ptr(pb), _ptr(sb), fn, user, C.byref(opt), C.byref(summ), log,
+                                          C.c_int(max_log), _ptr(steps), C.c_int64(steps.size)))
+    return dict(poses=pb, speed_bias=sb, summary=summ, iterations=iterations_to_dicts(log, min(summ.num_iterations, max_log)),
+                steps=steps[:summ.num_valid_steps])
+
+
+Context.window_solve = _window_solve

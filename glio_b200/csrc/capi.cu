@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "hostmath.h"
+#include "solver.h"
 
 using namespace glio;
 
@@ -222,6 +223,17 @@ EvalParams eval_params(const glio_ctx* c) {
   return ep;
 }
 
+// device evaluation of all active unary residuals -> c->h_out (W x 28: 21 upper-tri H, 6 g, 1 cost), synchronised
+void eval_unary_blocks(glio_ctx* c, int W, const double* poses_body, int jac_kind, bool want_jac) {
+  build_items(c, W);
+  memcpy(c->h_poses.p, poses_body, (size_t)W * 7 * sizeof(double));
+  GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_poses.p, c->h_poses.p, (size_t)W * 7 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  eval_unary_run(c->d_items.p, c->n_items, W, c->d_poses.p, eval_params(c), jac_kind, want_jac, c->d_partials.p, c->d_out.p,
+                 c->d_kf_item_start.p, c->d_ticket.p, c->st, c->lc);
+  GLIO_CUDA_TRY(cudaMemcpyAsync(c->h_out.p, c->d_out.p, (size_t)W * GLIO_NACC * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+}
+
 }  // namespace
 
 extern "C" {
@@ -407,14 +419,8 @@ int glio_eval_unary(glio_ctx* c, int W, const double* poses_body, int jac_kind, 
   return guarded(c, [&] {
     GLIO_REQUIRE(W > 0 && W <= 4096 && poses_body, GLIO_ERR_ARG, "bad arguments");
     GLIO_REQUIRE(jac_kind == 0 || jac_kind == 1, GLIO_ERR_ARG, "jac_kind must be 0 or 1");
-    build_items(c, W);
-    memcpy(c->h_poses.p, poses_body, (size_t)W * 7 * sizeof(double));
-    GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_poses.p, c->h_poses.p, (size_t)W * 7 * sizeof(double), cudaMemcpyHostToDevice, c->st));
     const bool want_jac = (H != nullptr) || (g != nullptr);
-    eval_unary_run(c->d_items.p, c->n_items, W, c->d_poses.p, eval_params(c), jac_kind, want_jac, c->d_partials.p, c->d_out.p,
-                   c->d_kf_item_start.p, c->d_ticket.p, c->st, c->lc);
-    GLIO_CUDA_TRY(cudaMemcpyAsync(c->h_out.p, c->d_out.p, (size_t)W * GLIO_NACC * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    eval_unary_blocks(c, W, poses_body, jac_kind, want_jac);
     for (int k = 0; k < W; ++k) {
       const double* o = c->h_out.p + (size_t)k * GLIO_NACC;
       if (H) {
@@ -424,6 +430,98 @@ int glio_eval_unary(glio_ctx* c, int W, const double* poses_body, int jac_kind, 
       if (g) for (int p = 0; p < 6; ++p) g[6 * k + p] = o[21 + p];
       if (cost) cost[k] = o[27];
     }
+  });
+}
+
+void glio_default_solver_options(glio_solver_options* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->max_num_iterations = 15; o->dogleg_type = 0; o->use_nonmonotonic_steps = 0; o->max_consecutive_nonmonotonic_steps = 5;
+  o->initial_trust_region_radius = 1e4; o->max_trust_region_radius = 1e16; o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3; o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32; o->max_num_consecutive_invalid_steps = 5;
+  o->jacobi_scaling = 1; o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+  o->fuse_candidate_jacobian = 1;
+}
+
+int glio_window_solve(glio_ctx* c, int W, double* poses, double* speed_bias, glio_host_factors_fn host_factors, void* user,
+                      const glio_solver_options* options, glio_solver_summary* summary, glio_iteration* iter_log, int iter_cap,
+                      double* step_log, int64_t step_cap) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(W > 0 && W <= 4096 && poses, GLIO_ERR_ARG, "bad arguments");
+    glio_solver_options o; if (options) o = *options; else glio_default_solver_options(&o);
+    const bool sb = speed_bias != nullptr;
+    const int nt = sb ? 15 : 6, na = sb ? 16 : 7, n = W * nt;
+    std::vector<ParamBlock> blocks;
+    for (int k = 0; k < W; ++k) {
+      blocks.push_back(ParamBlock{na * k, 3, nt * k, 3, false});
+      blocks.push_back(ParamBlock{na * k + 3, 4, nt * k + 3, 3, true});
+      if (sb) blocks.push_back(ParamBlock{na * k + 7, 9, nt * k + 6, 9, false});
+    }
+    SolverOptions so;
+    so.max_num_iterations = o.max_num_iterations; so.dogleg_type = o.dogleg_type; so.use_nonmonotonic_steps = o.use_nonmonotonic_steps != 0;
+    so.max_consecutive_nonmonotonic_steps = o.max_consecutive_nonmonotonic_steps;
+    so.initial_trust_region_radius = o.initial_trust_region_radius; so.max_trust_region_radius = o.max_trust_region_radius;
+    so.min_trust_region_radius = o.min_trust_region_radius; so.min_relative_decrease = o.min_relative_decrease;
+    so.min_lm_diagonal = o.min_lm_diagonal; so.max_lm_diagonal = o.max_lm_diagonal;
+    so.max_num_consecutive_invalid_steps = o.max_num_consecutive_invalid_steps; so.jacobi_scaling = o.jacobi_scaling != 0;
+    so.function_tolerance = o.function_tolerance; so.gradient_tolerance = o.gradient_tolerance; so.parameter_tolerance = o.parameter_tolerance;
+    so.fuse_candidate_jacobian = o.fuse_candidate_jacobian != 0;
+    TrustRegionDogleg solver(blocks, so);
+    std::vector<double> x((size_t)W * na), pz((size_t)W * 7), sz((size_t)W * 9);
+    for (int k = 0; k < W; ++k) {
+      for (int i = 0; i < 7; ++i) x[(size_t)na * k + i] = poses[7 * k + i];
+      if (sb) for (int i = 0; i < 9; ++i) x[(size_t)na * k + 7 + i] = speed_bias[9 * k + i];
+    }
+    EvalFn eval = [&](const double* xa, bool want_jac, double* cost, double* H, double* g) -> bool {
+      for (int k = 0; k < W; ++k) {
+        for (int i = 0; i < 7; ++i) pz[7 * k + i] = xa[(size_t)na * k + i];
+        if (sb) for (int i = 0; i < 9; ++i) sz[9 * k + i] = xa[(size_t)na * k + 7 + i];
+      }
+      eval_unary_blocks(c, W, pz.data(), 0, want_jac);
+      double ct = 0;
+      if (want_jac) { std::fill(H, H + (size_t)n * n, 0.0); std::fill(g, g + n, 0.0); }
+      for (int k = 0; k < W; ++k) {
+        const double* ob = c->h_out.p + (size_t)k * GLIO_NACC;
+        ct += ob[27];
+        if (want_jac) {
+          int idx = 0;
+          for (int p = 0; p < 6; ++p) for (int q = p; q < 6; ++q) {
+            H[(size_t)(nt * k + p) * n + nt * k + q] = ob[idx]; H[(size_t)(nt * k + q) * n + nt * k + p] = ob[idx]; ++idx;
+          }
+          for (int p = 0; p < 6; ++p) g[nt * k + p] = ob[21 + p];
+        }
+      }
+      if (host_factors) {
+        if (host_factors(user, W, pz.data(), sb ? sz.data() : nullptr, want_jac ? 1 : 0, H, g, &ct) != 0) return false;
+      }
+      *cost = ct;
+      return std::isfinite(ct);
+    };
+    SolverSummary S;
+    solver.solve(x.data(), eval, &S);
+    for (int k = 0; k < W; ++k) {
+      for (int i = 0; i < 7; ++i) poses[7 * k + i] = x[(size_t)na * k + i];
+      if (sb) for (int i = 0; i < 9; ++i) speed_bias[9 * k + i] = x[(size_t)na * k + 7 + i];
+    }
+    if (summary) {
+      memset(summary, 0, sizeof(*summary));
+      summary->termination = S.termination; summary->num_iterations = (int)S.iterations.size();
+      summary->num_successful_steps = S.num_successful_steps; summary->num_unsuccessful_steps = S.num_unsuccessful_steps;
+      summary->num_evaluations = S.num_evaluations; summary->num_jacobian_evaluations = S.num_jacobian_evaluations;
+      summary->num_linear_solves = S.num_linear_solves; summary->num_valid_steps = (int)(S.steps.size() / (size_t)n);
+      summary->initial_cost = S.initial_cost; summary->final_cost = S.final_cost;
+      snprintf(summary->message, sizeof(summary->message), "%s", S.message.c_str());
+    }
+    if (iter_log) for (int i = 0; i < (int)S.iterations.size() && i < iter_cap; ++i) {
+      const IterationRecord& r = S.iterations[i];
+      glio_iteration& q = iter_log[i];
+      q.iteration = r.iteration; q.step_is_valid = r.step_is_valid; q.step_is_successful = r.step_is_successful; q.reserved = 0;
+      q.cost = r.cost; q.cost_change = r.cost_change; q.gradient_max_norm = r.gradient_max_norm; q.gradient_norm = r.gradient_norm;
+      q.step_norm = r.step_norm; q.relative_decrease = r.relative_decrease; q.trust_region_radius = r.trust_region_radius; q.mu = r.mu;
+    }
+    if (step_log) memcpy(step_log, S.steps.data(), sizeof(double) * (size_t)std::min<int64_t>(step_cap, (int64_t)S.steps.size()));
+    GLIO_REQUIRE(S.termination != TERM_FAILURE || true, GLIO_ERR_NUMERIC, S.message);
   });
 }
 

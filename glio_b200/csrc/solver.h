@@ -1,0 +1,152 @@
+// solver.h — host-side trust-region (dogleg) minimizer over normal equations, with Ceres 2.0.0 semantics.
+//
+// The LiDAR residual blocks are evaluated on the device into 6x6 pose blocks; everything else the reference
+// adds to the same ceres::Problem (IMU, marginalisation prior, GNSS — host C++ CostFunctions by north_star)
+// arrives through a callback that accumulates into the same dense J^T J / J^T r.  This file restates, on the
+// normal equations, what ceres::Solve does for the options the reference sets (Estimator.cpp:2424-2433,
+// 3275-3284): TrustRegionMinimizer (ceres.tgz::internal/ceres/trust_region_minimizer.cc) with Jacobi scaling
+// (:231-263), DoglegStrategy (dogleg_strategy.cc:79-340,517-697; traditional and subspace),
+// normal-equation Cholesky (sparse_normal_cholesky_solver.cc:59-113), TrustRegionStepEvaluator
+// (trust_region_step_evaluator.cc) and QuaternionParameterization::Plus (local_parameterization.cc:163-182).
+// Quantities Ceres computes from the Jacobian itself (|J v|^2, (J s).(r + J s/2)) are computed from H = J^T J,
+// g = J^T r: identical in exact arithmetic, equal to rounding in floating point.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace glio {
+
+struct ParamBlock {
+  int amb_off, amb_size;   // offset/size in the ambient state vector
+  int tan_off, tan_size;   // offset/size in the tangent vector
+  bool quaternion;         // amb 4 (w,x,y,z) / tan 3, Ceres QuaternionParameterization
+};
+
+struct SolverOptions {
+  int max_num_iterations = 15;
+  int dogleg_type = 0;  // 0 TRADITIONAL_DOGLEG, 1 SUBSPACE_DOGLEG
+  bool use_nonmonotonic_steps = false;
+  int max_consecutive_nonmonotonic_steps = 5;
+  double initial_trust_region_radius = 1e4;
+  double max_trust_region_radius = 1e16;
+  double min_trust_region_radius = 1e-32;
+  double min_relative_decrease = 1e-3;
+  double min_lm_diagonal = 1e-6;
+  double max_lm_diagonal = 1e32;
+  int max_num_consecutive_invalid_steps = 5;
+  double function_tolerance = 1e-6;
+  double gradient_tolerance = 1e-10;
+  double parameter_tolerance = 1e-8;
+  bool jacobi_scaling = true;
+  int half_bandwidth = -1;   // >= 0: H is banded with this many sub-diagonals (batch); -1: dense
+  bool fuse_candidate_jacobian = true;  // evaluate J together with the candidate cost, reuse on acceptance
+};
+
+struct IterationRecord {
+  int iteration;
+  double cost, cost_change, gradient_max_norm, gradient_norm, step_norm, relative_decrease, trust_region_radius, mu;
+  int step_is_valid, step_is_successful;
+};
+
+enum Termination { TERM_CONVERGENCE = 0, TERM_NO_CONVERGENCE = 1, TERM_FAILURE = 2 };
+
+struct SolverSummary {
+  int termination = TERM_NO_CONVERGENCE;
+  std::string message;
+  double initial_cost = 0, final_cost = 0;
+  int num_successful_steps = 0, num_unsuccessful_steps = 0;
+  std::vector<IterationRecord> iterations;
+  std::vector<double> steps;   // tangent delta of every iteration that produced a valid step (n each), in order
+  int num_evaluations = 0, num_jacobian_evaluations = 0, num_linear_solves = 0;
+};
+
+// evaluate(x_ambient, want_jac, &cost, H (n*n row-major, overwritten, full symmetric), g (n, overwritten)) -> ok
+using EvalFn = std::function<bool(const double*, bool, double*, double*, double*)>;
+
+namespace detail {
+
+inline void quat_plus(const double* x, const double* d, double* o) {
+  const double nd = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  if (nd > 0.0) {
+    const double s = std::sin(nd) / nd;
+    const double z0 = std::cos(nd), z1 = s * d[0], z2 = s * d[1], z3 = s * d[2];
+    // ceres::QuaternionProduct(z, x)
+    o[0] = z0 * x[0] - z1 * x[1] - z2 * x[2] - z3 * x[3];
+    o[1] = z0 * x[1] + z1 * x[0] + z2 * x[3] - z3 * x[2];
+    o[2] = z0 * x[2] - z1 * x[3] + z2 * x[0] + z3 * x[1];
+    o[3] = z0 * x[3] + z1 * x[2] - z2 * x[1] + z3 * x[0];
+  } else {
+    o[0] = x[0]; o[1] = x[1]; o[2] = x[2]; o[3] = x[3];
+  }
+}
+
+// Cholesky of a symmetric positive definite matrix stored dense row-major (lower part used), optional band.
+// Returns false if a pivot is not positive / finite (Ceres: LINEAR_SOLVER_FAILURE -> mu escalation).
+inline bool cholesky_solve(std::vector<double>& A, int n, int hb, const double* b, double* x) {
+  auto lo = [&](int i) { return hb < 0 ? 0 : std::max(0, i - hb); };
+  for (int j = 0; j < n; ++j) {
+    double d = A[(size_t)j * n + j];
+    for (int k = lo(j); k < j; ++k) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+    if (!(d > 0.0) || !std::isfinite(d)) return false;
+    const double ljj = std::sqrt(d);
+    A[(size_t)j * n + j] = ljj;
+    const int imax = hb < 0 ? n : std::min(n, j + hb + 1);
+    for (int i = j + 1; i < imax; ++i) {
+      double s = A[(size_t)i * n + j];
+      const int k0 = std::max(lo(i), lo(j));
+      for (int k = k0; k < j; ++k) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+      A[(size_t)i * n + j] = s / ljj;
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    double s = b[i];
+    for (int k = lo(i); k < i; ++k) s -= A[(size_t)i * n + k] * x[k];
+    x[i] = s / A[(size_t)i * n + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = x[i];
+    const int kmax = hb < 0 ? n : std::min(n, i + hb + 1);
+    for (int k = i + 1; k < kmax; ++k) s -= A[(size_t)k * n + i] * x[k];
+    x[i] = s / A[(size_t)i * n + i];
+  }
+  for (int i = 0; i < n; ++i) if (!std::isfinite(x[i])) return false;
+  return true;
+}
+
+// real roots of a polynomial of degree <= 4 (highest power first), for the subspace dogleg
+// (dogleg_strategy.cc:421-446 uses FindPolynomialRoots; here: Durand-Kerner + Newton polish in long double).
+bool real_roots_deg4(const double* poly5, std::vector<double>* roots);
+
+}  // namespace detail
+
+class TrustRegionDogleg {
+ public:
+  TrustRegionDogleg(const std::vector<ParamBlock>& blocks, const SolverOptions& opt) : blocks_(blocks), opt_(opt) {
+    n_amb_ = 0; n_ = 0;
+    for (auto& b : blocks_) { n_amb_ = std::max(n_amb_, b.amb_off + b.amb_size); n_ = std::max(n_, b.tan_off + b.tan_size); }
+  }
+  int num_tangent() const { return n_; }
+  int num_ambient() const { return n_amb_; }
+
+  void plus(const double* x, const double* delta, double* out) const {
+    for (auto& b : blocks_) {
+      if (b.quaternion) detail::quat_plus(x + b.amb_off, delta + b.tan_off, out + b.amb_off);
+      else for (int k = 0; k < b.amb_size; ++k) out[b.amb_off + k] = x[b.amb_off + k] + delta[b.tan_off + k];
+    }
+  }
+
+  // x: ambient state, in/out (on return: the lowest-cost accepted point, like Ceres' `parameters`)
+  void solve(double* x_inout, const EvalFn& eval, SolverSummary* sum);
+
+ private:
+  std::vector<ParamBlock> blocks_;
+  SolverOptions opt_;
+  int n_amb_ = 0, n_ = 0;
+};
+
+}  // namespace glio

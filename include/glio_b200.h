@@ -119,6 +119,74 @@ int glio_eval_unary(glio_ctx* ctx, int W, const double* poses_body, int jac_kind
 int glio_eval_unary_residuals(glio_ctx* ctx, int slot, const double pose_body[7], int jac_kind, int64_t capacity,
                               double* r, double* J, int64_t* n);
 
+/* ---- the minimizer iteration around K2 (replaces ceres::Solve for the window problem, Estimator.cpp:2424-2433):
+ * Ceres 2.0.0 TrustRegionMinimizer + DoglegStrategy + Jacobi scaling + normal-equation Cholesky semantics
+ * (ceres.tgz::internal/ceres/{trust_region_minimizer,dogleg_strategy,trust_region_step_evaluator}.cc).
+ * LiDAR blocks come from the device; all other factors of the problem (IMU, marginalisation prior, GNSS — host C++
+ * by design) are added by the host_factors callback into the same dense tangent-space normal equations. */
+typedef struct {
+  int32_t max_num_iterations;            /* 15 (Estimator.cpp:2427); batch: max_num_iter */
+  int32_t dogleg_type;                   /* 0 TRADITIONAL_DOGLEG (window), 1 SUBSPACE_DOGLEG (batch, Estimator.cpp:3280) */
+  int32_t use_nonmonotonic_steps;        /* 0 window (Estimator.cpp:2430) / 1 batch (:3281) */
+  int32_t max_consecutive_nonmonotonic_steps; /* 5  (ceres solver.h:263) */
+  double initial_trust_region_radius;    /* 1e4  (solver.h:276) */
+  double max_trust_region_radius;        /* 1e16 */
+  double min_trust_region_radius;        /* 1e-32 */
+  double min_relative_decrease;          /* 1e-3 */
+  double min_lm_diagonal;                /* 1e-6 */
+  double max_lm_diagonal;                /* 1e32 */
+  int32_t max_num_consecutive_invalid_steps; /* 5 */
+  int32_t jacobi_scaling;                /* 1 */
+  double function_tolerance;             /* 1e-6 */
+  double gradient_tolerance;             /* 1e-10 */
+  double parameter_tolerance;            /* 1e-8 */
+  int32_t fuse_candidate_jacobian;       /* 1: evaluate J with the candidate cost and reuse it on acceptance (same numbers, one pass less) */
+  int32_t reserved;
+} glio_solver_options;
+void glio_default_solver_options(glio_solver_options* o);
+
+typedef struct {
+  int32_t iteration, step_is_valid, step_is_successful, reserved;
+  double cost, cost_change, gradient_max_norm, gradient_norm, step_norm, relative_decrease, trust_region_radius, mu;
+} glio_iteration;
+
+typedef struct {
+  int32_t termination;                   /* 0 CONVERGENCE, 1 NO_CONVERGENCE, 2 FAILURE */
+  int32_t num_iterations;                /* records written to the iteration log (iteration 0 included) */
+  int32_t num_successful_steps, num_unsuccessful_steps;
+  int32_t num_evaluations, num_jacobian_evaluations, num_linear_solves, num_valid_steps;
+  double initial_cost, final_cost;
+  char message[128];
+} glio_solver_summary;
+
+/* Adds the host-side factors at the given state.  n = W*(speed_bias ? 15 : 6), tangent order per keyframe
+ * [t(3), rotation(3), speed_bias(9)].  H (n*n row-major, full symmetric) and g (n) are ACCUMULATED INTO when
+ * want_jac != 0 (they already hold the LiDAR blocks); *cost is accumulated into.  Return 0 on success. */
+typedef int (*glio_host_factors_fn)(void* user, int W, const double* poses, const double* speed_bias, int want_jac,
+                                    double* H, double* g, double* cost);
+
+/* poses[W*7] (and speed_bias[W*9], may be NULL) are in/out: on return the lowest-cost accepted state, like the
+ * parameter blocks after ceres::Solve.  iter_log[iter_cap] and step_log[step_cap doubles: one n-vector per valid
+ * step, the tangent update Delta_k of SURVEY B.4] may be NULL. */
+int glio_window_solve(glio_ctx* ctx, int W, double* poses, double* speed_bias, glio_host_factors_fn host_factors, void* user,
+                      const glio_solver_options* options, glio_solver_summary* summary, glio_iteration* iter_log, int iter_cap,
+                      double* step_log, int64_t step_cap);
+
+/* ---- stand-in host factors (CPU C++, analytic) with the block structure of the reference's non-LiDAR factors:
+ * prior 15x[t,q,sb] (marginalisation-prior-like), between 15x[t,q,sb|t,q,sb] (IMU-chain-like), range 1x[t,q]
+ * (pseudorange-like).  glio_hf_evaluate has the glio_host_factors_fn signature (user = the set).  They exist so the
+ * plumbing of host factors + device LiDAR blocks can be tested and benchmarked without ROS / GNSS data; the real
+ * ImuFactor / MarginalizationFactor / dd_psr_factor plug in through the same callback (or the Ceres shim). */
+typedef struct glio_host_factor_set glio_host_factor_set;
+glio_host_factor_set* glio_hf_create(void);
+void glio_hf_destroy(glio_host_factor_set* s);
+void glio_hf_add_prior(glio_host_factor_set* s, int kf, const double t0[3], const double q0[4], const double* sb0 /*9 or NULL*/,
+                       const double sqrt_w[15]);
+void glio_hf_add_between(glio_host_factor_set* s, int i, int j, const double dp[3], const double dq[4], const double dv[3], double dt,
+                         const double sqrt_w[15]);
+void glio_hf_add_range(glio_host_factor_set* s, int kf, const double lever[3], const double sat[3], double rho, double w);
+int glio_hf_evaluate(void* user, int W, const double* poses, const double* speed_bias, int want_jac, double* H, double* g, double* cost);
+
 /* ---- K1b: scan-to-multiscan (batch) association.
  * Replaces findGlobalCorrespondingSurfFeatures_Batch / ...Add_Batch (Estimator.cpp:3710-3892).
  * Frames are registered once; a pair (cur, oth) associates every point of frame cur against frame oth. */

@@ -191,3 +191,83 @@ def quat_plus(x, delta):
 
 def quat_plus_jacobian(x):
     out = np.zeros(12); lib().go_quat_plus_jacobian(_p(_f64(x)), _p(out)); return out.reshape(4, 3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# window problem + Ceres-semantics solve (oracle/glio_oracle_solver.cpp)
+# ---------------------------------------------------------------------------------------------------
+class OSolverOptions(C.Structure):
+    _fields_ = [("max_num_iterations", C.c_int32), ("dogleg_type", C.c_int32), ("use_nonmonotonic_steps", C.c_int32),
+                ("max_consecutive_nonmonotonic_steps", C.c_int32), ("initial_trust_region_radius", C.c_double),
+                ("max_trust_region_radius", C.c_double), ("min_trust_region_radius", C.c_double),
+                ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
+                ("max_num_consecutive_invalid_steps", C.c_int32), ("jacobi_scaling", C.c_int32),
+                ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+                ("fuse_candidate_jacobian", C.c_int32), ("reserved", C.c_int32)]
+
+
+class OIteration(C.Structure):
+    _fields_ = [("iteration", C.c_int32), ("step_is_valid", C.c_int32), ("step_is_successful", C.c_int32), ("reserved", C.c_int32),
+                ("cost", C.c_double), ("cost_change", C.c_double), ("gradient_max_norm", C.c_double), ("gradient_norm", C.c_double),
+                ("step_norm", C.c_double), ("relative_decrease", C.c_double), ("trust_region_radius", C.c_double), ("mu", C.c_double)]
+
+
+class OSummary(C.Structure):
+    _fields_ = [("termination", C.c_int32), ("num_iterations", C.c_int32), ("num_successful_steps", C.c_int32),
+                ("num_unsuccessful_steps", C.c_int32), ("num_evaluations", C.c_int32), ("num_jacobian_evaluations", C.c_int32),
+                ("num_linear_solves", C.c_int32), ("num_valid_steps", C.c_int32), ("initial_cost", C.c_double),
+                ("final_cost", C.c_double), ("message", C.c_char * 128)]
+
+
+def solver_options(**kw):
+    # ceres.tgz::include/ceres/solver.h defaults + Estimator.cpp:2424-2433
+    o = OSolverOptions(15, 0, 0, 5, 1e4, 1e16, 1e-32, 1e-3, 1e-6, 1e32, 5, 1, 1e-6, 1e-10, 1e-8, 0, 0)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class WindowProblem:
+    def __init__(self, poses, speed_bias, q_lb, t_lb, huber_delta=1.0):
+        L = lib()
+        L.go_problem_create.restype = C.c_void_p
+        self.W = len(np.asarray(poses).reshape(-1, 7))
+        self.has_sb = speed_bias is not None
+        pb = _f64(poses).reshape(-1, 7); sb = None if speed_bias is None else _f64(speed_bias).reshape(-1, 9)
+        self.h = C.c_void_p(L.go_problem_create(C.c_int(self.W), _p(pb), _p(sb), _p(_f64(q_lb)), _p(_f64(t_lb)), C.c_double(huber_delta)))
+        self.n = self.W * (15 if self.has_sb else 6)
+
+    def add_unary(self, kf, cp, nsd, score):
+        kf = np.ascontiguousarray(kf, np.int32); cp = _f32(cp).reshape(-1, 3); nsd = _f32(nsd).reshape(-1, 4); score = _f64(score)
+        lib().go_problem_add_unary(self.h, C.c_int64(len(kf)), _p(kf), _p(cp), _p(nsd), _p(score))
+
+    def add_prior(self, kf, t0, q0, sb0, sqrt_w):
+        lib().go_problem_add_prior(self.h, C.c_int(kf), _p(_f64(t0)), _p(_f64(q0)), _p(None if sb0 is None else _f64(sb0)), _p(_f64(sqrt_w)))
+
+    def add_between(self, i, j, dp, dq, dv, dt, sqrt_w):
+        lib().go_problem_add_between(self.h, C.c_int(i), C.c_int(j), _p(_f64(dp)), _p(_f64(dq)), _p(_f64(dv)), C.c_double(dt), _p(_f64(sqrt_w)))
+
+    def add_range(self, kf, lever, sat, rho, w):
+        lib().go_problem_add_range(self.h, C.c_int(kf), _p(_f64(lever)), _p(_f64(sat)), C.c_double(rho), C.c_double(w))
+
+    def host_normal_eq(self):
+        H = np.zeros((self.n, self.n)); g = np.zeros(self.n); c = np.zeros(1)
+        lib().go_problem_host_normal_eq(self.h, _p(H), _p(g), _p(c))
+        return H, g, float(c[0])
+
+    def solve(self, options=None, mode=0, nthreads=1, max_log=256):
+        opt = options or solver_options()
+        summ = OSummary(); log = (OIteration * max_log)(); steps = np.zeros((max_log, self.n))
+        lib().go_problem_solve(self.h, C.byref(opt), C.c_int(mode), C.c_int(nthreads), C.byref(summ), log, C.c_int(max_log), _p(steps), C.c_int64(steps.size))
+        poses = np.zeros((self.W, 7)); sb = np.zeros((self.W, 9)) if self.has_sb else None
+        lib().go_problem_get_state(self.h, _p(poses), _p(sb))
+        names = [f[0] for f in OIteration._fields_ if f[0] != "reserved"]
+        its = [{k: getattr(log[i], k) for k in names} for i in range(min(summ.num_iterations, max_log))]
+        return dict(poses=poses, speed_bias=sb, summary=summ, iterations=its, steps=steps[:summ.num_valid_steps])
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().go_problem_free(self.h); self.h = None
+        except Exception:
+            pass
