@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — sliding-window FGO iterations/sec on BASELINE.json cfg 2 (W=20 keyframes, 100k surf pts/scan, 1M-point
+local map, scan-to-map surf association + Ceres-semantics dogleg solve), B200 vs the CPU restatement.
+
+One "step" = one complete optimizeSlidingWindowWithLandMark LiDAR pass (GLIO/src/Estimator.cpp:2046-2460):
+  K0 grid build over the local map  ->  K1 association of all W scans  ->  minimizer iterations
+  (K2 residual/Jacobian/normal-equation kernel + host factors + Cholesky + dogleg) until Ceres' own
+  convergence tests stop it.
+metric value = minimizer iterations executed / time, whole job (association amortised into it).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+N>1 is launched by torchrun (one rank per GPU).  The window path does not shard (20 independent 6x6
+blocks and a 300x300 solve) -> "replicas only": every rank solves its own window; value is the sum over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(W=20, Q=100_000, M=1_000_000)
+METRIC = "sliding-window FGO iterations/sec (20 KF, 100k surf pts/scan)"
+
+
+def host_factor_spec(P, rng):
+    """IMU-chain-like between factors + a prior on keyframe 0 + speed/bias states (15 tangent dims per keyframe,
+    the block structure of the reference window problem, Estimator.cpp:2130-2192)."""
+    from glio_b200 import synth
+    T = P["poses_true"]; W = len(T)
+    sw = np.concatenate([np.full(3, 20.0), np.full(3, 50.0), np.full(9, 5.0)])
+    spec = dict(prior=(0, T[0, :3].copy(), T[0, 3:].copy(), np.zeros(9), sw), between=[])
+    for i in range(W - 1):
+        dq = synth.quat_mul(synth.quat_conj(T[i, 3:]), T[i + 1, 3:])
+        dp = synth.quat_to_R(T[i, 3:]).T @ (T[i + 1, :3] - T[i, :3])
+        spec["between"].append((i, i + 1, dp + rng.normal(0, 0.01, 3), dq, np.zeros(3), 0.1, sw * 0.5))
+    return spec
+
+
+def start_clock_sampler(dev_index):
+    f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False); f.close()
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(dev_index)],
+                             stdout=open(f.name, "w"), stderr=subprocess.DEVNULL)
+    except Exception:
+        return None, f.name
+    return p, f.name
+
+
+def stop_clock_sampler(p, path):
+    out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+    if p is not None:
+        p.terminate()
+        try:
+            p.wait(timeout=5)
+        except Exception:
+            p.kill()
+    try:
+        rows = [r.strip().split(",") for r in open(path) if r.strip()]
+        sm = [float(r[1]) for r in rows if len(r) >= 9]
+        if sm:
+            out["sm_mhz"] = float(np.median(sm)); out["sm_max_mhz"] = float(rows[0][2])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for k, nm in enumerate(names):
+                if any("Active" == r[5 + k].strip() and "Not" not in r[5 + k] for r in rows if len(r) >= 9):
+                    out["reasons"].append(nm)
+            out["samples"] = len(sm)
+    except Exception:
+        pass
+    try:
+        os.unlink(path)
+    except Exception:
+        pass
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference path) on host cores
+# ----------------------------------------------------------------------------------------------------------
+def cpu_solve_once(P, spec, nthreads, q_sub=1):
+    """One full reference-style window pass on the CPU oracle.  Returns (iterations, seconds, detail)."""
+    from oracle import pyoracle as po
+    from glio_b200 import synth
+    t0 = time.perf_counter()
+    tree = po.KdTree(P["map_xyz"])                                        # setInputCloud (Estimator.cpp:2056)
+    t_tree = time.perf_counter() - t0
+    W = len(P["scans"])
+    prob = po.WindowProblem(P["poses_init"], np.zeros((W, 9)), P["q_lb"], P["t_lb"], huber_delta=1.0)
+    nres = 0
+    for k in range(W):
+        t2, q2 = synth.lidar_pose_in_world(P["poses_init"][k, :3], P["poses_init"][k, 3:])
+        scan = P["scans"][k][::q_sub]
+        o = po.assoc_scan_to_map(P["map_xyz"], scan, t2, q2, tree=tree, nthreads=nthreads)   # Estimator.cpp:2222
+        v = o["status"] == po.GO_VALID
+        prob.add_unary(np.full(int(v.sum()), k, np.int32), scan[v], o["nsd"][v], o["score"][v])
+        nres += int(v.sum())
+    t_assoc = time.perf_counter() - t0 - t_tree
+    prob.add_prior(*spec["prior"])
+    for b in spec["between"]:
+        prob.add_between(*b)
+    r = prob.solve(po.solver_options(), mode=0, nthreads=nthreads)       # ceres::Solve (Estimator.cpp:2433)
+    dt = time.perf_counter() - t0
+    iters = len(r["steps"])
+    return iters, dt, dict(kdtree_s=round(t_tree, 3), assoc_s=round(t_assoc, 3), solve_s=round(dt - t_tree - t_assoc, 3), residuals=nres)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: Eigen/Ceres/PCL are absent
+    from this image so oracle/_ref cannot be built — DESIGN.md) on all host threads."""
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    from glio_b200 import synth
+    po.build()
+    cores = os.cpu_count() or 1
+    P = synth.window_problem(**CFG, seed=synth.SEED0 + 2)
+    spec = host_factor_spec(P, np.random.default_rng(1))
+    # bounded sample: every q_sub-th point of every scan (kd-tree over the full 1M map), so that warmup+steps end in minutes
+    q_sub = args.ref_subsample
+    tot_it, tot_t, detail = 0, 0.0, None
+    for s in range(args.warmup + args.steps):
+        it, dt, detail = cpu_solve_once(P, spec, cores, q_sub)
+        if s >= args.warmup:
+            tot_it += it; tot_t += dt
+    value = tot_it / tot_t
+    line = dict(impl="reference", metric=METRIC, value=value, unit="iterations/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * tot_t / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                data="synthetic", config=dict(workload="cfg2: optimizeSlidingWindow, W=20, Q=100k/scan, M=1M, no selection", **CFG),
+                cpu_baseline=dict(value=value, unit="iterations/s", cores=cores, kind="port",
+                                  sample=f"full window pass per step with every {q_sub}-th scan point (kd-tree on the full map); {detail}"),
+                e2e=dict(value=value, unit="iterations/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def run_glio(args, rank, world, local_rank):
+    import torch
+    from glio_b200 import api, synth
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    P = synth.window_problem(**CFG, seed=synth.SEED0 + 2 + rank)
+    spec = host_factor_spec(P, np.random.default_rng(1 + rank))
+    W = CFG["W"]
+    ctx = api.Context(local_rank)
+    hf = api.HostFactorSet()
+    hf.add_prior(*spec["prior"])
+    for b in spec["between"]:
+        hf.add_between(*b)
+    sb0 = np.zeros((W, 9))
+    st = torch.cuda.ExternalStream(ctx.stream)
+    # resident inputs (value) and pinned host inputs (e2e)
+    dmap = torch.from_numpy(P["map_xyz"]).cuda(); dscans = [torch.from_numpy(s).cuda() for s in P["scans"]]
+    pmap = torch.from_numpy(P["map_xyz"]).pin_memory(); pscans = [torch.from_numpy(s).pin_memory() for s in P["scans"]]
+    hmap = pmap.numpy(); hscans = [s.numpy() for s in pscans]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    opts = api.default_solver_options()
+
+    def one_step(m, scans):
+        ctx.set_map(m)
+        ctx.window_set_scans(scans)
+        ctx.window_associate(P["poses_init"])
+        r = ctx.window_solve(P["poses_init"], sb0, hf, opts)
+        return len(r["steps"]), r
+
+    def timed_run(m, scans, nsteps):
+        iters = 0
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(st)
+        for _ in range(nsteps):
+            with torch.cuda.stream(st):
+                flush.fill_(1)                      # L2 flush between steps (256 MB > 126 MB L2), inside the timed region
+            it, _ = one_step(m, scans)
+            iters += it
+        e1.record(st)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        if dist is not None:
+            dist.barrier()
+        return iters, ms, wall
+
+    for _ in range(max(args.warmup, 3)):
+        one_step(dmap, dscans)
+    ctx.lib_profile(True)
+    ctx.knn_fallback_queries(reset=True)
+    sampler, spath = start_clock_sampler(local_rank) if rank == 0 else (None, None)
+    l0 = ctx.launch_count
+    iters, ms, wall = timed_run(dmap, dscans, args.steps)
+    launches = ctx.launch_count - l0
+    clocks = stop_clock_sampler(sampler, spath) if rank == 0 else None
+    prof = ctx.lib_profile_read()
+    n_fallback = ctx.knn_fallback_queries()
+    ctx.lib_profile(False)
+    for _ in range(2):
+        one_step(hmap, hscans)
+    iters_e, ms_e, wall_e = timed_run(hmap, hscans, args.steps)
+    _, rlast = one_step(dmap, dscans)
+
+    tmax, tmax_e, it_sum, it_sum_e = ms, ms_e, iters, iters_e
+    if dist is not None:
+        t = torch.tensor([ms, ms_e], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); tmax, tmax_e = t.tolist()
+        c = torch.tensor([iters, iters_e], device="cuda", dtype=torch.float64); dist.all_reduce(c); it_sum, it_sum_e = c.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    value = it_sum / (tmax * 1e-3)
+    e2e = it_sum_e / (tmax_e * 1e-3)
+    # roofline of the dominant kernel (K1 association): algorithmic bytes = 116*Qt + 12*M per launch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+    Qt = CFG["W"] * CFG["Q"]
+    kern = {}
+    for name, (tot_ms, cnt) in prof.items():
+        kern[name] = dict(ms_total=round(tot_ms, 4), launches=cnt, ms_avg=round(tot_ms / max(cnt, 1), 5))
+    roof = None
+    if "k_knn_search" in prof and "k_plane_fit" in prof:
+        # K1 is one association pass issued as two launches (warp-cooperative search, then the fp64 plane fit)
+        avg_ms = prof["k_knn_search"][0] / prof["k_knn_search"][1] + prof["k_plane_fit"][0] / prof["k_plane_fit"][1]
+        alg = 116.0 * Qt + 12.0 * CFG["M"]
+        ach = alg / (avg_ms * 1e-3) / 1e9
+        roof = dict(bound="hbm", kernel="K1 association pass = k_knn_search + k_plane_fit (exact 5-NN + plane fit + gates)",
+                    achieved=round(ach, 2), peak=peak, unit="GB/s", frac=round(ach / peak, 5), traffic=None, algorithmic_bytes=alg,
+                    avg_ms=round(avg_ms, 5), peak_source=peak_src)
+    if "k_eval_unary" in prof and prof["k_eval_unary"][1] > 0:
+        avg_ms2 = prof["k_eval_unary"][0] / prof["k_eval_unary"][1]
+        nres = int(rlast["summary"].num_iterations and sum(ctx.get_match_counts(W)))
+        kern["k_eval_unary"]["achieved_GBps"] = round(32.0 * nres / (avg_ms2 * 1e-3) / 1e9, 2)
+        kern["k_eval_unary"]["frac_of_peak"] = round(kern["k_eval_unary"]["achieved_GBps"] / peak, 5)
+        kern["k_eval_unary"]["residuals"] = nres
+    # CPU baseline (oracle port), 1 thread = the reference's own setting (options.num_threads = 1, Estimator.cpp:2426)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import pyoracle as po
+        po.build()
+        q_sub = args.cpu_subsample
+        it_c, dt_c, det = cpu_solve_once(P, spec, 1, q_sub)
+        cpu = dict(value=it_c / dt_c, unit="iterations/s", cores=1, kind="port",
+                   sample=f"one full window pass (kd-tree build on the 1M map + association + solve) with every {q_sub}-th scan point; {det}")
+    s = rlast["summary"]
+    h2d = 12 * CFG["M"] + 12 * Qt + 8 * 7 * W * (s.num_evaluations + 1)
+    d2h = 8 * 28 * W * s.num_evaluations + 4 * W + 8 * 7 * W
+    line = dict(metric=METRIC, value=value, unit="iterations/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=tmax / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload="cfg2: optimizeSlidingWindow, W=20, Q=100k/scan, M=1M, no selection, +prior/IMU-like host factors (15 dims/KF)",
+                            **CFG, iterations_per_step=it_sum / args.steps / world, residuals=int(sum(ctx.get_match_counts(W))),
+                            parallelism="replicas only (window path does not shard)" if world > 1 else "1 GPU",
+                            l2="256 MB flush between steps inside the timed region; per-step working set ~300 MB > 126 MB L2; "
+                               "K2 re-reads the 64 MB residual table every iteration as the real solve does",
+                            host_wall_ms_per_step=1e3 * wall / args.steps, knn_fallback_queries_per_step=n_fallback / args.steps, kernels=kern),
+                e2e=dict(value=e2e, unit="iterations/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=tmax_e / args.steps),
+                gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="glio", choices=["glio", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-subsample", type=int, default=1, help="cpu_baseline leg: use every n-th scan point")
+    ap.add_argument("--ref-subsample", type=int, default=1, help="--impl reference: use every n-th scan point")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_glio(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

@@ -131,6 +131,32 @@ class Context:
         self._lib.glio_lidar_pose(C.byref(self.params), _ptr(pb), _ptr(t2), _ptr(q2))
         return t2, q2
 
+    KERNELS = ["k_knn_search", "k_plane_fit", "k_plane_fit_pair", "k_eval_unary", "k_eval_unary_cost", "k_transform_hist", "k_order_scatter",
+               "k_compact", "k_flags", "k_cell_hist", "k_cell_scatter", "k_load_bounds", "k_scan_block", "k_scan_add",
+               "k_eval_binary", "k_eval_binary_cost", "k_bin_assemble"]
+
+    def lib_profile(self, on):
+        self._chk(self._lib.glio_profile_enable(self._h, C.c_int(1 if on else 0)))
+
+    def lib_profile_read(self):
+        out = {}
+        for k in self.KERNELS:
+            ms = C.c_double(0); n = C.c_int64(0)
+            self._chk(self._lib.glio_profile_get(self._h, k.encode(), C.byref(ms), C.byref(n)))
+            if n.value:
+                out[k] = (ms.value, int(n.value))
+        return out
+
+    def knn_fallback_queries(self, reset=False):
+        n = C.c_int64(0)
+        self._chk(self._lib.glio_get_stats(self._h, C.byref(n), C.c_int(1 if reset else 0)))
+        return int(n.value)
+
+    def get_match_counts(self, W, active=True):
+        nm = np.zeros(W, np.int64); na = np.zeros(W, np.int64)
+        self._chk(self._lib.glio_get_match_counts(self._h, C.c_int(W), _ptr(nm), _ptr(na)))
+        return na if active else nm
+
     # ---- K0
     def set_map(self, xyz):
         keep, p, n, stride, mem = _points_arg(xyz)

@@ -72,67 +72,135 @@ __device__ __forceinline__ void top5_push(Top5& t, float d, int id) {
   }
 }
 
-__device__ __forceinline__ void scan_range(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz, Top5& t) {
-  for (int k = s; k < e; ++k) {
-    const float4 p = __ldg(&pts[k]);
-    top5_push(t, l2_simple(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
-  }
-}
+// ---------------------------------------------------------------------------------------------------
+// K1a: warp-cooperative exact 5-NN.
+// Queries arrive sorted by grid cell, so the 32 queries of a warp sit in a short run of x-adjacent cells of one
+// (y,z) row.  The warp stages the rows around that run — each row is ONE contiguous range of the counting-sorted
+// map (x is the fastest cell coordinate) — through shared memory with coalesced 16-byte loads, and every lane scans
+// the same candidate list (broadcast LDS, uniform trip count: no divergence).  The scanned box grows ring by ring
+// (shell cells only, nothing is visited twice) until every lane's 5th distance is provably inside the box, or the
+// box covers the gate radius (anything unseen then fails the radius gate anyway).
+// Intermediate results are written in sorted order, structure-of-arrays: coalesced here and in K1b.
+// ---------------------------------------------------------------------------------------------------
+constexpr int KNN_WARPS = 4;
+constexpr int KNN_SPAN_MAX = 12;
 
-// Exact 5-NN of (qx,qy,qz) in the grid.  Guarantee: if the true 5th squared distance is < gate (+margin) the
-// returned five are exact; otherwise t.d4 >= gate (the caller's radius gate fails either way).
-__device__ __forceinline__ void knn5_grid(const GridDesc& g, float qx, float qy, float qz, float gate_sq, Top5& t) {
-  const float INF = __int_as_float(0x7f800000);
-  t.d0 = t.d1 = t.d2 = t.d3 = t.d4 = INF;
-  t.i0 = t.i1 = t.i2 = t.i3 = t.i4 = 0x7fffffff;
-  const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
-  // number of rings that covers sqrt(gate) with a safety margin (mis-binning by float rounding < 1e-3 m)
-  const int rmax = (int)ceilf((sqrtf(gate_sq) + 2e-3f) * g.inv_cell) + 1;
-  // far outside the grid: nothing within the gate
-  if (cx < -rmax || cy < -rmax || cz < -rmax || cx >= g.nx + rmax || cy >= g.ny + rmax || cz >= g.nz + rmax) return;
-  const int* __restrict__ cs = g.cell_start;
-  for (int r = 1; r <= rmax; ++r) {
-    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.nz - 1);
-    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.ny - 1);
-    const int xa = cx - r, xb = cx + r;
-    const int x0 = max(xa, 0), x1 = min(xb, g.nx - 1);
-    for (int z = z0; z <= z1; ++z) {
-      const bool zshell = (z == cz - r) || (z == cz + r);
-      for (int y = y0; y <= y1; ++y) {
-        const int row = (z * g.ny + y) * g.nx;
-        const bool shell = r == 1 || zshell || (y == cy - r) || (y == cy + r);
-        if (shell) {
-          if (x0 <= x1) scan_range(g.pts, __ldg(&cs[row + x0]), __ldg(&cs[row + x1 + 1]), qx, qy, qz, t);
-        } else {
-          if (xa >= 0 && xa < g.nx) scan_range(g.pts, __ldg(&cs[row + xa]), __ldg(&cs[row + xa + 1]), qx, qy, qz, t);
-          if (xb >= 0 && xb < g.nx) scan_range(g.pts, __ldg(&cs[row + xb]), __ldg(&cs[row + xb + 1]), qx, qy, qz, t);
-        }
-      }
-    }
-    // distance from the query to the faces of the searched cube (faces clipped by the grid are infinitely far:
-    // nothing lives outside the grid)
-    float b = INF;
-    if (cx - r > 0)        b = fminf(b, qx - (g.ox + (float)(cx - r) * g.cell));
-    if (cx + r < g.nx - 1) b = fminf(b, (g.ox + (float)(cx + r + 1) * g.cell) - qx);
-    if (cy - r > 0)        b = fminf(b, qy - (g.oy + (float)(cy - r) * g.cell));
-    if (cy + r < g.ny - 1) b = fminf(b, (g.oy + (float)(cy + r + 1) * g.cell) - qy);
-    if (cz - r > 0)        b = fminf(b, qz - (g.oz + (float)(cz - r) * g.cell));
-    if (cz + r < g.nz - 1) b = fminf(b, (g.oz + (float)(cz + r + 1) * g.cell) - qz);
-    if (b == INF) return;                       // the cube covers the whole grid
-    const float bs = b * 0.999f - 2e-3f;        // safety: float rounding of cell assignment / face positions
-    if (bs > 0.f && t.d4 <= bs * bs) return;    // 5th neighbour provably inside the cube
-  }
-}
-
-struct KnnArgs {
+struct SearchArgs {
   GridDesc grid;
-  const SegDesc* segs;
   int64_t Qt;
   const float4* pm;
-  const uint16_t* segid;
   const uint32_t* order;
+  float gate_sq;
+  int32_t* knn_idx;     // [5][Qt] sorted order
+  float* knn_sqd;       // [5][Qt] sorted order
+  unsigned long long* n_fallback;
+};
+
+__global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
+  __shared__ float4 stage[KNN_WARPS][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t p = ((int64_t)blockIdx.x * KNN_WARPS + wid) * 32 + lane;
+  const bool active = p < a.Qt;
+  const GridDesc& G = a.grid;
+  const float INF = __int_as_float(0x7f800000);
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (active) { const float4 q4 = a.pm[a.order[p]]; qx = q4.x; qy = q4.y; qz = q4.z; }
+  const int cx = cell_coord(qx, G.ox, G.inv_cell), cy = cell_coord(qy, G.oy, G.inv_cell), cz = cell_coord(qz, G.oz, G.inv_cell);
+  Top5 t;
+  t.d0 = t.d1 = t.d2 = t.d3 = t.d4 = INF;
+  t.i0 = t.i1 = t.i2 = t.i3 = t.i4 = 0x7fffffff;
+  const int rmax = (int)ceilf((sqrtf(a.gate_sq) + 2e-3f) * G.inv_cell) + 1;
+  // far outside the grid: nothing within the gate radius
+  const bool far_out = cx < -rmax || cy < -rmax || cz < -rmax || cx >= G.nx + rmax || cy >= G.ny + rmax || cz >= G.nz + rmax;
+  bool done = !active || far_out;
+  const int* __restrict__ cs = G.cell_start;
+  unsigned long long extra_rings = 0;
+  for (;;) {
+    const unsigned pending = __ballot_sync(0xffffffffu, !done);
+    if (!pending) break;
+    const int leader = __ffs(pending) - 1;
+    const int lcx = __shfl_sync(0xffffffffu, cx, leader), lcy = __shfl_sync(0xffffffffu, cy, leader), lcz = __shfl_sync(0xffffffffu, cz, leader);
+    const bool part = !done && cy == lcy && cz == lcz && cx >= lcx && cx < lcx + KNN_SPAN_MAX;
+    const int hix = __reduce_max_sync(0xffffffffu, part ? cx : lcx);
+    bool unproven = part;
+    for (int r = 1; r <= rmax; ++r) {
+      const int xa = lcx - r, xb = hix + r;                 // scanned cell range in x after this ring
+      const int x0 = max(xa, 0), x1 = min(xb, G.nx - 1);
+      const int z0 = max(lcz - r, 0), z1 = min(lcz + r, G.nz - 1);
+      const int y0 = max(lcy - r, 0), y1 = min(lcy + r, G.ny - 1);
+      for (int z = z0; z <= z1; ++z) {
+        const bool zshell = (z == lcz - r) || (z == lcz + r);
+        for (int y = y0; y <= y1; ++y) {
+          const int row = (z * G.ny + y) * G.nx;
+          const bool shell = r == 1 || zshell || (y == lcy - r) || (y == lcy + r);
+          // shell rows are new: whole x-range; inner rows were scanned up to [xa+1, xb-1]: only the two end cells
+          for (int part_i = 0; part_i < 2; ++part_i) {
+            int s, e;
+            if (shell) { if (part_i == 1 || x0 > x1) break; s = __ldg(&cs[row + x0]); e = __ldg(&cs[row + x1 + 1]); }
+            else {
+              const int xc = part_i == 0 ? xa : xb;
+              if (xc < 0 || xc >= G.nx) continue;
+              s = __ldg(&cs[row + xc]); e = __ldg(&cs[row + xc + 1]);
+            }
+            for (int base = s; base < e; base += 32) {
+              const int k = base + lane;
+              if (k < e) stage[wid][lane] = __ldg(&G.pts[k]);
+              __syncwarp();
+              const int cnt = min(32, e - base);
+              if (unproven) {
+                for (int j = 0; j < cnt; ++j) {
+                  const float4 c = stage[wid][j];
+                  top5_push(t, l2_simple(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+      if (unproven) {
+        // distance to the faces of the scanned box; faces clipped by the grid are infinitely far (nothing lives outside)
+        float b = INF;
+        if (xa > 0)               b = fminf(b, qx - (G.ox + (float)xa * G.cell));
+        if (xb < G.nx - 1)        b = fminf(b, (G.ox + (float)(xb + 1) * G.cell) - qx);
+        if (lcy - r > 0)          b = fminf(b, qy - (G.oy + (float)(lcy - r) * G.cell));
+        if (lcy + r < G.ny - 1)   b = fminf(b, (G.oy + (float)(lcy + r + 1) * G.cell) - qy);
+        if (lcz - r > 0)          b = fminf(b, qz - (G.oz + (float)(lcz - r) * G.cell));
+        if (lcz + r < G.nz - 1)   b = fminf(b, (G.oz + (float)(lcz + r + 1) * G.cell) - qz);
+        const float bs = b * 0.999f - 2e-3f;   // safety: float rounding of cell assignment / face positions
+        if ((b == INF) || (bs > 0.f && t.d4 <= bs * bs)) unproven = false;
+        else ++extra_rings;
+      }
+      if (!__ballot_sync(0xffffffffu, unproven)) break;
+    }
+    if (part) done = true;
+  }
+  if (a.n_fallback) {
+    for (int o = 16; o > 0; o >>= 1) extra_rings += __shfl_xor_sync(0xffffffffu, extra_rings, o);
+    if (lane == 0 && extra_rings) atomicAdd(a.n_fallback, extra_rings);
+  }
+  if (active) {
+    a.knn_idx[0 * a.Qt + p] = t.i0; a.knn_idx[1 * a.Qt + p] = t.i1; a.knn_idx[2 * a.Qt + p] = t.i2;
+    a.knn_idx[3 * a.Qt + p] = t.i3; a.knn_idx[4 * a.Qt + p] = t.i4;
+    a.knn_sqd[0 * a.Qt + p] = t.d0; a.knn_sqd[1 * a.Qt + p] = t.d1; a.knn_sqd[2 * a.Qt + p] = t.d2;
+    a.knn_sqd[3 * a.Qt + p] = t.d3; a.knn_sqd[4 * a.Qt + p] = t.d4;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1b: gate -> plane fit (fp64 column-pivoted Householder QR) -> validity -> weight -> outputs.
+// One thread per query, in sorted order (neighbour gathers of adjacent threads hit the same lines).
+// ---------------------------------------------------------------------------------------------------
+struct FitArgs {
+  int64_t Qt;
+  const float4* pm;
+  const uint32_t* order;
+  const int32_t* knn_idx;
+  const float* knn_sqd;
   AssocGates gates;
-  // outputs
+  const float4* pts_by_idx;   // searched cloud, original order (x,y,z,idx)
+  const float* oth_local;     // pair mode: local-frame points of the searched frame (original order)
+  int oth_stride;
   uint8_t* status;
   float4* nsd;
   float* weight;
@@ -140,27 +208,23 @@ struct KnnArgs {
   int32_t* idx5;
   float* sqd5;
   double* plane;
-  // pair mode: local-frame points of the searched frame (original order)
-  const float* oth_local;
-  int oth_stride;
-  // original-order world points of the searched cloud are recovered from grid.pts via idx? no: see pts_by_idx
-  const float4* pts_by_idx;   // unsorted float4 copy (x,y,z,idx) of the searched cloud, original order
 };
 
 template <bool PAIR>
-__global__ void __launch_bounds__(128) k_knn_plane(KnnArgs a) {
+__global__ void __launch_bounds__(128) k_plane_fit(FitArgs a) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.Qt) return;
   const int64_t g = a.order[p];
   const float4 q4 = a.pm[g];
-  Top5 t;
-  knn5_grid(a.grid, q4.x, q4.y, q4.z, (float)a.gates.max_radius, t);
-  int id[5] = {t.i0, t.i1, t.i2, t.i3, t.i4};
+  int id[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) id[j] = a.knn_idx[(int64_t)j * a.Qt + p];
+  const float d4 = a.knn_sqd[4 * a.Qt + p];
   uint8_t st;
   float w = 0.f;
   double n[3] = {0, 0, 0}, d = 0;
   double nl[3] = {0, 0, 0}, cl[3] = {0, 0, 0};
-  if (t.i4 != 0x7fffffff && (double)t.d4 < a.gates.max_radius) {          // Estimator.cpp:3651 / :3751
+  if (id[4] != 0x7fffffff && (double)d4 < a.gates.max_radius) {           // Estimator.cpp:3651 / :3751
     double A[3][5];
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -218,9 +282,11 @@ __global__ void __launch_bounds__(128) k_knn_plane(KnnArgs a) {
   }
   a.weight[g] = (st == GLIO_MATCH_VALID || st == GLIO_MATCH_FAIL_WEIGHT) ? w : 0.f;
   if (a.idx5) {
-    const float sd[5] = {t.d0, t.d1, t.d2, t.d3, t.d4};
 #pragma unroll
-    for (int j = 0; j < 5; ++j) { a.idx5[5 * g + j] = (id[j] == 0x7fffffff) ? -1 : id[j]; a.sqd5[5 * g + j] = sd[j]; }
+    for (int j = 0; j < 5; ++j) {
+      a.idx5[5 * g + j] = (id[j] == 0x7fffffff) ? -1 : id[j];
+      a.sqd5[5 * g + j] = a.knn_sqd[(int64_t)j * a.Qt + p];
+    }
     a.plane[4 * g] = n[0]; a.plane[4 * g + 1] = n[1]; a.plane[4 * g + 2] = n[2]; a.plane[4 * g + 3] = d;
   }
 }
@@ -231,26 +297,32 @@ void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const Assoc
   const GridDesc& grid = gb.desc;
   const int64_t Qt = w.Qt;
   if (Qt <= 0) return;
-  GLIO_REQUIRE(Qt < ((int64_t)1 << 32), GLIO_ERR_ARG, "assoc_run: too many queries in one launch");
+  GLIO_REQUIRE(Qt < ((int64_t)1 << 31), GLIO_ERR_ARG, "assoc_run: too many queries in one launch");
   GLIO_REQUIRE(nseg > 0 && nseg < 65536, GLIO_ERR_ARG, "assoc_run: bad segment count");
   const int64_t ncell = (int64_t)grid.nx * grid.ny * grid.nz;
   cell_count.reserve((size_t)ncell + 2);
   cell_pos.reserve((size_t)ncell + 2);
   GLIO_CUDA_TRY(cudaMemsetAsync(cell_count.p, 0, (size_t)(ncell + 1) * sizeof(int), st));
   const unsigned nb = (unsigned)((Qt + 255) / 256);
-  k_transform_hist<<<nb, 256, 0, st>>>(grid, d_segs, nseg, Qt, w.pm, w.seg, cell_count.p); lc.n++;
+  lc.begin("k_transform_hist", st); k_transform_hist<<<nb, 256, 0, st>>>(grid, d_segs, nseg, Qt, w.pm, w.seg, cell_count.p); lc.end(st);
   exclusive_scan_i32(cell_count.p, cell_pos.p, ncell + 1, scan_tmp, st, lc);
   GLIO_CUDA_TRY(cudaMemsetAsync(cell_count.p, 0, (size_t)(ncell + 1) * sizeof(int), st));
-  k_order_scatter<<<nb, 256, 0, st>>>(grid, Qt, w.pm, cell_pos.p, cell_count.p, w.order); lc.n++;
-  KnnArgs a;
-  a.grid = grid; a.segs = d_segs; a.Qt = Qt; a.pm = w.pm; a.segid = w.seg; a.order = w.order; a.gates = gates;
-  a.status = w.status; a.nsd = w.nsd; a.weight = w.weight; a.normal_cent = w.normal_cent;
-  a.idx5 = w.idx5; a.sqd5 = w.sqd5; a.plane = w.plane;
-  a.oth_local = oth_local; a.oth_stride = oth_stride; a.pts_by_idx = gb.tmp4.p;
+  lc.begin("k_order_scatter", st); k_order_scatter<<<nb, 256, 0, st>>>(grid, Qt, w.pm, cell_pos.p, cell_count.p, w.order); lc.end(st);
+  SearchArgs sa;
+  sa.grid = grid; sa.Qt = Qt; sa.pm = w.pm; sa.order = w.order; sa.gate_sq = (float)gates.max_radius;
+  sa.knn_idx = w.knn_idx; sa.knn_sqd = w.knn_sqd; sa.n_fallback = w.n_fallback;
+  const unsigned ns = (unsigned)((Qt + 32 * KNN_WARPS - 1) / (32 * KNN_WARPS));
+  lc.begin("k_knn_search", st); k_knn_search<<<ns, 32 * KNN_WARPS, 0, st>>>(sa); lc.end(st);
+  FitArgs fa;
+  fa.Qt = Qt; fa.pm = w.pm; fa.order = w.order; fa.knn_idx = w.knn_idx; fa.knn_sqd = w.knn_sqd; fa.gates = gates;
+  fa.pts_by_idx = gb.tmp4.p; fa.oth_local = oth_local; fa.oth_stride = oth_stride;
+  fa.status = w.status; fa.nsd = w.nsd; fa.weight = w.weight; fa.normal_cent = w.normal_cent;
+  fa.idx5 = w.idx5; fa.sqd5 = w.sqd5; fa.plane = w.plane;
   const unsigned nk = (unsigned)((Qt + 127) / 128);
-  if (w.normal_cent) { k_knn_plane<true><<<nk, 128, 0, st>>>(a); }
-  else { k_knn_plane<false><<<nk, 128, 0, st>>>(a); }
-  lc.n++;
+  lc.begin(w.normal_cent ? "k_plane_fit_pair" : "k_plane_fit", st);
+  if (w.normal_cent) k_plane_fit<true><<<nk, 128, 0, st>>>(fa);
+  else k_plane_fit<false><<<nk, 128, 0, st>>>(fa);
+  lc.end(st);
   GLIO_CUDA_TRY(cudaGetLastError());
 }
 
@@ -292,10 +364,10 @@ void compact_run(const AssocWork& w, const SegDesc* d_segs, int nseg, int* d_fla
                  const void* d_dst /*CompactDst[nseg]*/, int* d_counts, cudaStream_t st, LaunchCounter& lc) {
   const int64_t Qt = w.Qt;
   const unsigned nb = (unsigned)((Qt + 1 + 255) / 256);
-  k_flags<<<nb, 256, 0, st>>>(w.status, Qt, d_flags); lc.n++;
+  lc.begin("k_flags", st); k_flags<<<nb, 256, 0, st>>>(w.status, Qt, d_flags); lc.end(st);
   exclusive_scan_i32(d_flags, d_pos, Qt + 1, scan_tmp, st, lc);
-  k_seg_counts<<<(nseg + 127) / 128, 128, 0, st>>>(d_segs, nseg, d_pos, d_counts); lc.n++;
-  k_compact<<<nb, 256, 0, st>>>(d_segs, Qt, w.seg, w.status, d_pos, w.nsd, w.weight, w.normal_cent, (const CompactDst*)d_dst); lc.n++;
+  lc.begin("k_seg_counts", st); k_seg_counts<<<(nseg + 127) / 128, 128, 0, st>>>(d_segs, nseg, d_pos, d_counts); lc.end(st);
+  lc.begin("k_compact", st); k_compact<<<nb, 256, 0, st>>>(d_segs, Qt, w.seg, w.status, d_pos, w.nsd, w.weight, w.normal_cent, (const CompactDst*)d_dst); lc.end(st);
   GLIO_CUDA_TRY(cudaGetLastError());
 }
 
@@ -319,7 +391,7 @@ __global__ void __launch_bounds__(256) k_gather_sel(const int32_t* __restrict__ 
 void gather_selection(const int32_t* d_keep, int64_t n, int64_t n_match, const float4* cpw, const float4* nsd, const double* nc,
                       float4* o_cpw, float4* o_nsd, double* o_nc, int* d_bad, cudaStream_t st, LaunchCounter& lc) {
   if (n <= 0) return;
-  k_gather_sel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_keep, n, n_match, cpw, nsd, nc, o_cpw, o_nsd, o_nc, d_bad); lc.n++;
+  lc.begin("k_gather_sel", st); k_gather_sel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_keep, n, n_match, cpw, nsd, nc, o_cpw, o_nsd, o_nc, d_bad); lc.end(st);
   GLIO_CUDA_TRY(cudaGetLastError());
 }
 

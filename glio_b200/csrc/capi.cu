@@ -44,6 +44,7 @@ struct glio_ctx {
   std::string err;
   LaunchCounter lc;
 
+  float pts_per_cell = 16.0f;   // target points per occupied grid cell (tuning hook: env GLIO_PTS_PER_CELL)
   GridBuild map;
   bool has_map = false;
   DevBuf<float> map_stage;
@@ -59,6 +60,9 @@ struct glio_ctx {
   DevBuf<double> w_nc, w_plane;
   DevBuf<int32_t> w_idx5;
   DevBuf<float> w_sqd5;
+  DevBuf<int32_t> w_knn_idx;
+  DevBuf<float> w_knn_sqd;
+  DevBuf<unsigned long long> d_stats;
   DevBuf<int> w_flags, w_pos, cell_count, cell_pos, scan_tmp;
   DevBuf<SegDesc> d_segs;
   DevBuf<CompactDst> d_dst;
@@ -120,6 +124,8 @@ void ensure_work(glio_ctx* c, int64_t Qt, bool pair) {
   c->w_pm.reserve((size_t)Qt); c->w_seg.reserve((size_t)Qt); c->w_order.reserve((size_t)Qt);
   c->w_status.reserve((size_t)Qt); c->w_weight.reserve((size_t)Qt);
   c->w_flags.reserve((size_t)Qt + 1); c->w_pos.reserve((size_t)Qt + 1);
+  c->w_knn_idx.reserve((size_t)Qt * 5); c->w_knn_sqd.reserve((size_t)Qt * 5);
+  if (!c->d_stats.p) { c->d_stats.reserve(4); GLIO_CUDA_TRY(cudaMemsetAsync(c->d_stats.p, 0, 4 * sizeof(unsigned long long), c->st)); }
   if (pair) c->w_nc.reserve((size_t)Qt * 6); else c->w_nsd.reserve((size_t)Qt);
   if (c->prm.keep_debug) { c->w_idx5.reserve((size_t)Qt * 5); c->w_sqd5.reserve((size_t)Qt * 5); c->w_plane.reserve((size_t)Qt * 4); }
 }
@@ -127,6 +133,7 @@ void ensure_work(glio_ctx* c, int64_t Qt, bool pair) {
 AssocWork make_work(glio_ctx* c, int64_t Qt, bool pair) {
   AssocWork w{};
   w.Qt = Qt; w.pm = c->w_pm.p; w.seg = c->w_seg.p; w.order = c->w_order.p; w.status = c->w_status.p;
+  w.knn_idx = c->w_knn_idx.p; w.knn_sqd = c->w_knn_sqd.p; w.n_fallback = c->d_stats.p;
   w.nsd = pair ? nullptr : c->w_nsd.p; w.weight = c->w_weight.p; w.normal_cent = pair ? c->w_nc.p : nullptr;
   if (c->prm.keep_debug) { w.idx5 = c->w_idx5.p; w.sqd5 = c->w_sqd5.p; w.plane = c->w_plane.p; }
   return w;
@@ -260,6 +267,7 @@ int glio_create(int device, const glio_params* params, glio_ctx** out) {
     c = new glio_ctx();
     c->device = device;
     if (params) c->prm = *params; else glio_default_params(&c->prm);
+    if (const char* e = getenv("GLIO_PTS_PER_CELL")) { const float v = (float)atof(e); if (v > 0.1f && v < 1000.f) c->pts_per_cell = v; }
     GLIO_CUDA_TRY(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
   });
   if (rc != GLIO_OK) { delete c; return rc; }
@@ -278,7 +286,7 @@ void glio_destroy(glio_ctx* c) {
   c->cell_count.release(); c->cell_pos.release(); c->scan_tmp.release(); c->d_segs.release(); c->d_dst.release(); c->d_counts.release();
   c->h_counts.release(); c->d_bad.release(); c->d_keep.release(); c->d_items.release(); c->d_kf_item_start.release();
   c->d_partials.release(); c->d_out.release(); c->d_poses.release(); c->d_r.release(); c->d_J.release(); c->h_out.release();
-  c->h_poses.release(); c->d_ticket.release();
+  c->h_poses.release(); c->d_ticket.release(); c->w_knn_idx.release(); c->w_knn_sqd.release(); c->d_stats.release();
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
@@ -292,6 +300,55 @@ int glio_synchronize(glio_ctx* c) {
 void* glio_stream(glio_ctx* c) { return c ? (void*)c->st : nullptr; }
 int64_t glio_launch_count(const glio_ctx* c) { return c ? c->lc.n : 0; }
 
+int glio_profile_enable(glio_ctx* c, int on) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    for (auto& r : c->lc.recs) { c->lc.pool.push_back(r.a); c->lc.pool.push_back(r.b); }
+    c->lc.recs.clear();
+    c->lc.prof = on != 0;
+  });
+}
+
+int glio_profile_get(glio_ctx* c, const char* kernel_name, double* ms_total, int64_t* launches) {
+  if (!c || !kernel_name) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    double tot = 0; int64_t cnt = 0;
+    for (auto& r : c->lc.recs) {
+      if (strcmp(r.name, kernel_name) != 0) continue;
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { tot += ms; ++cnt; }
+    }
+    if (ms_total) *ms_total = tot;
+    if (launches) *launches = cnt;
+  });
+}
+
+int glio_get_stats(glio_ctx* c, int64_t* knn_fallback_queries, int reset) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if (c->d_stats.p) {
+      GLIO_CUDA_TRY(cudaMemcpyAsync(h, c->d_stats.p, sizeof(h), cudaMemcpyDeviceToHost, c->st));
+      GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+      if (reset) GLIO_CUDA_TRY(cudaMemsetAsync(c->d_stats.p, 0, sizeof(h), c->st));
+    }
+    if (knn_fallback_queries) *knn_fallback_queries = (int64_t)h[0];
+  });
+}
+
+int glio_get_match_counts(glio_ctx* c, int W, int64_t* n_match, int64_t* n_active) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    for (int k = 0; k < W; ++k) {
+      Slot& sl = c->slot(k);
+      if (n_match) n_match[k] = sl.n_match;
+      if (n_active) n_active[k] = sl.n_sel >= 0 ? sl.n_sel : sl.n_match;
+    }
+  });
+}
+
 void glio_lidar_pose(const glio_params* prm, const double pose_body[7], double t2[3], double q2[4]) {
   lidar_pose_in_map(prm->q_lb, prm->t_lb, pose_body, t2, q2);
 }
@@ -301,7 +358,7 @@ int glio_set_map(glio_ctx* c, const float* xyz, int64_t M, int stride, int mem) 
   return guarded(c, [&] {
     GLIO_REQUIRE(M >= 5, GLIO_ERR_ARG, "map needs at least 5 points");
     const float* d = stage_points(c, c->map_stage, xyz, M, stride, mem);
-    grid_build(c->map, d, stride, M, nullptr, nullptr, c->prm.cell_size, 3.0f, c->st, c->lc);
+    grid_build(c->map, d, stride, M, nullptr, nullptr, c->prm.cell_size, c->pts_per_cell, c->st, c->lc);
     c->has_map = true;
   });
 }

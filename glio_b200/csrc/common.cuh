@@ -106,6 +106,9 @@ struct AssocWork {
   float4* pm;           // transformed query (x,y,z, _)
   uint16_t* seg;        // segment id of the query
   uint32_t* order;      // queries sorted by grid cell
+  int32_t* knn_idx;     // [5][Qt] neighbour indices, sorted order (K1a -> K1b)
+  float* knn_sqd;       // [5][Qt] squared distances, sorted order
+  unsigned long long* n_fallback;  // statistics: queries that needed the per-thread ring search
   uint8_t* status;
   float4* nsd;          // weight*n, weight*d   (scan-to-map)
   float* weight;
@@ -132,7 +135,25 @@ struct EvalItem {
   int32_t kf;
 };
 
-struct LaunchCounter { int64_t n = 0; };
+// Launch bookkeeping: counts every kernel launch (bench "gpu_launches") and, when profiling is enabled, brackets
+// each launch with CUDA events on the launching stream so per-kernel device time can be read back
+// (bench.py roofline: measured live inside the timed region).
+struct LaunchCounter {
+  int64_t n = 0;
+  bool prof = false;
+  struct Rec { const char* name; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get_event() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void begin(const char* name, cudaStream_t st) {
+    ++n;
+    if (prof) { Rec r{name, get_event(), get_event()}; cudaEventRecord(r.a, st); recs.push_back(r); }
+  }
+  void end(cudaStream_t st) { if (prof && !recs.empty()) cudaEventRecord(recs.back().b, st); }
+};
 
 // ---- K0 (grid.cu)
 struct GridBuild {

@@ -173,10 +173,11 @@ void eval_unary_run(const EvalItem* d_items, int nitems, int W, const double* d_
     GLIO_CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)W * NACC * sizeof(double), st));
     return;
   }
+  lc.begin(want_jac ? "k_eval_unary" : "k_eval_unary_cost", st);
   if (!want_jac) k_eval_unary<false, 0><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, d_poses, ep, d_partials, d_out, d_kf_item_start, d_ticket);
   else if (jac_kind == 0) k_eval_unary<true, 0><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, d_poses, ep, d_partials, d_out, d_kf_item_start, d_ticket);
   else k_eval_unary<true, 1><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, d_poses, ep, d_partials, d_out, d_kf_item_start, d_ticket);
-  lc.n++;
+  lc.end(st);
   GLIO_CUDA_TRY(cudaGetLastError());
 }
 
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256) k_unary_residuals(const float4* __restric
 void eval_unary_residuals_run(const float4* cpw, const float4* nsd, int64_t n, const double* d_pose, const EvalParams& ep,
                               int jac_kind, double* d_r, double* d_J, cudaStream_t st, LaunchCounter& lc) {
   if (n <= 0) return;
-  k_unary_residuals<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cpw, nsd, n, d_pose, ep, jac_kind, d_r, d_J); lc.n++;
+  lc.begin("k_unary_residuals", st); k_unary_residuals<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cpw, nsd, n, d_pose, ep, jac_kind, d_r, d_J); lc.end(st);
   GLIO_CUDA_TRY(cudaGetLastError());
 }
 

@@ -70,13 +70,13 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_add(int* __restrict__ out, cons
 static void scan_rec(const int* in, int* out, int64_t n, int* tmp, int64_t tmp_cap, cudaStream_t st, LaunchCounter& lc) {
   const int64_t nb = (n + SCAN_B - 1) / SCAN_B;
   if (nb <= 1) {
-    k_scan_block<<<1, SCAN_T, 0, st>>>(in, out, nullptr, n); lc.n++;
+    lc.begin("k_scan_block", st); k_scan_block<<<1, SCAN_T, 0, st>>>(in, out, nullptr, n); lc.end(st);
     return;
   }
   GLIO_REQUIRE(nb <= tmp_cap, GLIO_ERR_STATE, "scan scratch too small");
-  k_scan_block<<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, tmp, n); lc.n++;
+  lc.begin("k_scan_block", st); k_scan_block<<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, tmp, n); lc.end(st);
   scan_rec(tmp, tmp, nb, tmp + nb, tmp_cap - nb, st, lc);
-  k_scan_add<<<(unsigned)nb, SCAN_T, 0, st>>>(out, tmp, n); lc.n++;
+  lc.begin("k_scan_add", st); k_scan_add<<<(unsigned)nb, SCAN_T, 0, st>>>(out, tmp, n); lc.end(st);
 }
 
 void exclusive_scan_i32(const int* in, int* out, int64_t n, DevBuf<int>& tmp, cudaStream_t st, LaunchCounter& lc) {
@@ -167,9 +167,9 @@ void grid_build(GridBuild& gb, const float* d_xyz, int stride, int64_t n, const 
   int has_pose = 0;
   if (t && q) { has_pose = 1; for (int k = 0; k < 3; ++k) pose.t[k] = t[k]; for (int k = 0; k < 4; ++k) pose.q[k] = q[k]; }
   int* d_bounds = (int*)gb.bounds.p;
-  k_init_bounds<<<1, 32, 0, st>>>(d_bounds); lc.n++;
+  lc.begin("k_init_bounds", st); k_init_bounds<<<1, 32, 0, st>>>(d_bounds); lc.end(st);
   const int nb = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
-  k_load_bounds<<<nb, 256, 0, st>>>(d_xyz, stride, n, pose, has_pose, gb.tmp4.p, d_bounds); lc.n++;
+  lc.begin("k_load_bounds", st); k_load_bounds<<<nb, 256, 0, st>>>(d_xyz, stride, n, pose, has_pose, gb.tmp4.p, d_bounds); lc.end(st);
   int hb[6];
   GLIO_CUDA_TRY(cudaMemcpyAsync(hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
   GLIO_CUDA_TRY(cudaStreamSynchronize(st));
@@ -204,10 +204,10 @@ void grid_build(GridBuild& gb, const float* d_xyz, int stride, int64_t n, const 
   gb.cell_start.reserve((size_t)ncell + 2);
   gb.fill.reserve((size_t)ncell + 2);
   GLIO_CUDA_TRY(cudaMemsetAsync(gb.fill.p, 0, (size_t)(ncell + 1) * sizeof(int), st));
-  k_cell_hist<<<nb, 256, 0, st>>>(gb.tmp4.p, n, g, gb.fill.p); lc.n++;
+  lc.begin("k_cell_hist", st); k_cell_hist<<<nb, 256, 0, st>>>(gb.tmp4.p, n, g, gb.fill.p); lc.end(st);
   exclusive_scan_i32(gb.fill.p, gb.cell_start.p, ncell + 1, gb.scan_tmp, st, lc);
   GLIO_CUDA_TRY(cudaMemsetAsync(gb.fill.p, 0, (size_t)(ncell + 1) * sizeof(int), st));
-  k_cell_scatter<<<nb, 256, 0, st>>>(gb.tmp4.p, n, g, gb.cell_start.p, gb.fill.p, gb.pts.p); lc.n++;
+  lc.begin("k_cell_scatter", st); k_cell_scatter<<<nb, 256, 0, st>>>(gb.tmp4.p, n, g, gb.cell_start.p, gb.fill.p, gb.pts.p); lc.end(st);
   GLIO_CUDA_TRY(cudaGetLastError());
   g.cell_start = gb.cell_start.p;
   g.pts = gb.pts.p;

@@ -67,8 +67,11 @@ namespace {
 inline double dot(const std::vector<double>& a, const std::vector<double>& b) { double s = 0; for (size_t i = 0; i < a.size(); ++i) s += a[i] * b[i]; return s; }
 inline double norm(const std::vector<double>& a) { return std::sqrt(dot(a, a)); }
 // y = A x for symmetric dense A
-inline void symv(const std::vector<double>& A, int n, const std::vector<double>& x, std::vector<double>& y) {
-  for (int i = 0; i < n; ++i) { double s = 0; const double* r = &A[(size_t)i * n]; for (int j = 0; j < n; ++j) s += r[j] * x[j]; y[i] = s; }
+inline void symv(const std::vector<double>& A, int n, int hb, const std::vector<double>& x, std::vector<double>& y) {
+  for (int i = 0; i < n; ++i) {
+    const int j0 = hb < 0 ? 0 : std::max(0, i - hb), j1 = hb < 0 ? n : std::min(n, i + hb + 1);
+    double s = 0; const double* r = &A[(size_t)i * n]; for (int j = j0; j < j1; ++j) s += r[j] * x[j]; y[i] = s;
+  }
 }
 
 // trust_region_step_evaluator.cc
@@ -109,10 +112,12 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
   double sub_B[4] = {0, 0, 0, 0}, sub_g[2] = {0, 0};
   bool sub_1d = false;
 
+  int hb = opt_.half_bandwidth;   // half bandwidth of H (detected from the sparsity pattern at iteration 0 when < 0)
   auto apply_scaling = [&]() {
     for (int i = 0; i < n; ++i) {
       const double si = scale[i];
-      for (int j = 0; j < n; ++j) Hs[(size_t)i * n + j] = H[(size_t)i * n + j] * si * scale[j];
+      const int j0 = hb < 0 ? 0 : std::max(0, i - hb), j1 = hb < 0 ? n : std::min(n, i + hb + 1);
+      for (int j = j0; j < j1; ++j) Hs[(size_t)i * n + j] = H[(size_t)i * n + j] * si * scale[j];
       gs[i] = g[i] * si;
     }
   };
@@ -210,7 +215,7 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
     sub_g[0] = dot(basis0, grad_d); sub_g[1] = dot(basis1, grad_d);
     for (int i = 0; i < n; ++i) { tmp[i] = basis0[i] / diag[i]; tmp2[i] = basis1[i] / diag[i]; }
     std::vector<double> h0(n), h1(n);
-    symv(Hs, n, tmp, h0); symv(Hs, n, tmp2, h1);
+    symv(Hs, n, hb, tmp, h0); symv(Hs, n, hb, tmp2, h1);
     sub_B[0] = dot(tmp, h0); sub_B[1] = dot(tmp, h1); sub_B[2] = sub_B[1]; sub_B[3] = dot(tmp2, h1);
     return true;
   };
@@ -221,7 +226,7 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
     for (int i = 0; i < n; ++i) diag[i] = std::sqrt(std::min(std::max(Hs[(size_t)i * n + i], opt_.min_lm_diagonal), opt_.max_lm_diagonal));
     for (int i = 0; i < n; ++i) grad_d[i] = gs[i] / diag[i];
     for (int i = 0; i < n; ++i) tmp[i] = grad_d[i] / diag[i];
-    symv(Hs, n, tmp, tmp2);
+    symv(Hs, n, hb, tmp, tmp2);
     alpha = dot(grad_d, grad_d) / dot(tmp, tmp2);
     bool ok = false;
     while (mu < max_mu) {
@@ -229,7 +234,7 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
       const double sm = std::sqrt(mu);
       for (int i = 0; i < n; ++i) { const double lm = diag[i] * sm; A[(size_t)i * n + i] += lm * lm; }
       S.num_linear_solves++;
-      if (detail::cholesky_solve(A, n, opt_.half_bandwidth, gs.data(), y.data())) { ok = true; break; }
+      if (detail::cholesky_solve(A, n, hb, gs.data(), y.data())) { ok = true; break; }
       mu *= mu_inc;
     }
     if (!ok) return 1;
@@ -247,6 +252,13 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
     S.termination = TERM_FAILURE; S.message = "Residual and Jacobian evaluation failed."; return;
   }
   S.initial_cost = x_cost; S.final_cost = x_cost;
+  if (hb < 0) {
+    // the block structure of the problem is fixed, so the band of J^T J is too: factor only inside it
+    // (window: prior + IMU chain + unary LiDAR blocks -> block tridiagonal; a dense coupling simply yields hb = n-1)
+    int w = 0;
+    for (int i = 0; i < n; ++i) for (int j = 0; j < i - w; ++j) if (H[(size_t)i * n + j] != 0.0 || H[(size_t)j * n + i] != 0.0) { w = i - j; break; }
+    hb = w;
+  }
   if (opt_.jacobi_scaling) for (int i = 0; i < n; ++i) scale[i] = 1.0 / (1.0 + std::sqrt(H[(size_t)i * n + i]));
   apply_scaling();
   it.cost = x_cost; gradient_norms(it);
@@ -274,7 +286,7 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
     const int rc = compute_step();
     bool valid = false;
     if (rc == 0) {
-      symv(Hs, n, step, tmp);
+      symv(Hs, n, hb, step, tmp);
       model_cost_change = -(dot(step, gs) + 0.5 * dot(step, tmp));
       valid = model_cost_change > 0.0;
       if (valid) { for (int i = 0; i < n; ++i) delta[i] = step[i] * scale[i]; num_consecutive_invalid = 0; }

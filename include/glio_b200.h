@@ -72,6 +72,17 @@ void* glio_stream(glio_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py "gpu_launches") */
 int64_t glio_launch_count(const glio_ctx* ctx);
 
+/* per-kernel device time: when enabled every launch is bracketed by CUDA events on the context's stream;
+ * glio_profile_get sums the elapsed time of all launches of the named kernel since profiling was enabled
+ * (names: k_knn_plane, k_knn_plane_pair, k_eval_unary, k_eval_unary_cost, k_transform_hist, k_order_scatter,
+ * k_compact, k_cell_hist, k_cell_scatter, k_load_bounds, k_scan_block, k_scan_add, k_eval_binary, ...). */
+int glio_profile_enable(glio_ctx* ctx, int on);
+int glio_profile_get(glio_ctx* ctx, const char* kernel_name, double* ms_total, int64_t* launches);
+/* statistics: number of queries whose 5-NN needed the per-thread ring search (outside the warp-cooperative fast path) */
+int glio_get_stats(glio_ctx* ctx, int64_t* knn_fallback_queries, int reset);
+/* vec_surf_res_cnt for slots 0..W-1 (all matches) and the number currently active (after glio_select) */
+int glio_get_match_counts(glio_ctx* ctx, int W, int64_t* n_match, int64_t* n_active);
+
 /* lidar->map pose of a keyframe:  Q2 = Q * q_lb^-1 ; T2 = T - Q2 * t_lb   (Estimator.cpp:2216-2217) */
 void glio_lidar_pose(const glio_params* prm, const double pose_body[7], double t2[3], double q2[4]);
 
