@@ -337,3 +337,118 @@ def _window_solve(self, poses, speed_bias=None, host_factors=None, options=None,
 
 
 Context.window_solve = _window_solve
+
+
+# ---------------------------------------------------------------------------------------------------
+# batch (scan-to-multiscan) path
+# ---------------------------------------------------------------------------------------------------
+def _batch_set_frame(self, frame, scan_xyz, pose):
+    keep, p, n, stride, mem = _points_arg(scan_xyz)
+    if not hasattr(self, "_frame_keep"):
+        self._frame_keep = {}
+    self._frame_keep[frame] = keep
+    ps = np.ascontiguousarray(pose, np.float64)
+    self._chk(self._lib.glio_batch_set_frame(self._h, C.c_int(frame), p, C.c_int64(n), C.c_int(stride), C.c_int(mem), _ptr(ps)))
+
+
+def _batch_set_pose(self, frame, pose):
+    ps = np.ascontiguousarray(pose, np.float64)
+    self._chk(self._lib.glio_batch_set_pose(self._h, C.c_int(frame), _ptr(ps)))
+
+
+def _batch_associate_pairs(self, cur, oth):
+    cur = np.ascontiguousarray(cur, np.int32); oth = np.ascontiguousarray(oth, np.int32)
+    nm = np.zeros(len(cur), np.int64)
+    self._chk(self._lib.glio_batch_associate_pairs(self._h, _ptr(cur), _ptr(oth), C.c_int64(len(cur)), _ptr(nm)))
+    return nm
+
+
+def _batch_get_matches(self, cur, oth, capacity):
+    cp = np.empty((capacity, 3), np.float32); w = np.empty(capacity, np.float32); nc = np.empty((capacity, 6), np.float64)
+    src = np.empty(capacity, np.int32); n = C.c_int64(0)
+    self._chk(self._lib.glio_batch_get_matches(self._h, C.c_int(cur), C.c_int(oth), C.c_int64(capacity), _ptr(cp), _ptr(w), _ptr(nc), _ptr(src), C.byref(n)))
+    n = int(n.value)
+    return dict(cp=cp[:n], weight=w[:n], normal_cent=nc[:n], src=src[:n], n=n)
+
+
+def _batch_select(self, cur, oth, keep):
+    if keep is None:
+        self._chk(self._lib.glio_batch_select(self._h, C.c_int(cur), C.c_int(oth), None, C.c_int64(-1)))
+        return
+    k = np.ascontiguousarray(keep, np.int32)
+    self._chk(self._lib.glio_batch_select(self._h, C.c_int(cur), C.c_int(oth), _ptr(k), C.c_int64(len(k))))
+
+
+def _batch_pair_list(self):
+    n = C.c_int64(0)
+    self._chk(self._lib.glio_batch_pair_list(self._h, C.c_int64(0), None, None, C.byref(n)))
+    cur = np.zeros(n.value, np.int32); oth = np.zeros(n.value, np.int32)
+    self._chk(self._lib.glio_batch_pair_list(self._h, C.c_int64(n.value), _ptr(cur), _ptr(oth), C.byref(n)))
+    return cur, oth
+
+
+def _batch_clear(self):
+    self._chk(self._lib.glio_batch_clear(self._h))
+
+
+def _eval_binary(self, poses, want_jac=True):
+    pb = np.ascontiguousarray(poses, np.float64).reshape(-1, 7); K = len(pb)
+    n = C.c_int64(0)
+    self._chk(self._lib.glio_batch_pair_list(self._h, C.c_int64(0), None, None, C.byref(n)))
+    P = int(n.value)
+    Hd = np.zeros((K, 6, 6)) if want_jac else None; Ho = np.zeros((P, 6, 6)) if want_jac else None
+    g = np.zeros((K, 6)) if want_jac else None; cost = np.zeros(1)
+    self._chk(self._lib.glio_eval_binary(self._h, C.c_int(K), _ptr(pb), _ptr(Hd), _ptr(Ho), _ptr(g), _ptr(cost)))
+    return dict(Hdiag=Hd, Hoff=Ho, g=g, cost=float(cost[0]))
+
+
+HOST_FACTORS_BAND_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,
+                                   C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double))
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+
+def batch_solver_options(**kw):
+    """Estimator.cpp:3275-3281: SUBSPACE_DOGLEG, nonmonotonic steps, max_num_iter (100 in the shipped yaml)."""
+    base = dict(dogleg_type=1, use_nonmonotonic_steps=1, max_num_iterations=100)
+    base.update(kw)
+    return default_solver_options(**base)
+
+
+def _batch_declare_pairs(self, cur, oth):
+    cur = np.ascontiguousarray(cur, np.int32); oth = np.ascontiguousarray(oth, np.int32)
+    self._chk(self._lib.glio_batch_declare_pairs(self._h, _ptr(cur), _ptr(oth), C.c_int64(len(cur))))
+
+
+def _batch_solve(self, poses, speed_bias=None, host_factors=None, options=None, max_log=256):
+    pb = np.array(poses, np.float64).reshape(-1, 7).copy(); K = len(pb)
+    sb = None if speed_bias is None else np.array(speed_bias, np.float64).reshape(K, 9).copy()
+    n = K * (15 if sb is not None else 6)
+    opt = options if options is not None else batch_solver_options()
+    summ = SolverSummary(); log = (Iteration * max_log)(); steps = np.zeros((max_log, n))
+    if host_factors is None:
+        fn, user = C.cast(None, HOST_FACTORS_BAND_FN), None
+    else:
+        fn, user = C.cast(self._lib.glio_hf_evaluate_band, HOST_FACTORS_BAND_FN), host_factors._h
+    self._chk(self._lib.glio_batch_solve(self._h, C.c_int(K), _ptr(pb), _ptr(sb), fn, user, C.byref(opt), C.byref(summ), log,
+                                         C.c_int(max_log), _ptr(steps), C.c_int64(steps.size)))
+    return dict(poses=pb, speed_bias=sb, summary=summ, iterations=iterations_to_dicts(log, min(summ.num_iterations, max_log)),
+                steps=steps[:summ.num_valid_steps])
+
+
+def _set_allreduce(self, fn, user=None):
+    """fn: an ALLREDUCE_FN instance (or a raw function pointer from libglio_nccl.so); keeps a reference alive."""
+    self._allreduce_keep = (fn, user)
+    self._chk(self._lib.glio_set_allreduce(self._h, fn, user))
+
+
+Context.batch_declare_pairs = _batch_declare_pairs
+Context.batch_solve = _batch_solve
+Context.set_allreduce = _set_allreduce
+Context.batch_set_frame = _batch_set_frame
+Context.batch_set_pose = _batch_set_pose
+Context.batch_associate_pairs = _batch_associate_pairs
+Context.batch_get_matches = _batch_get_matches
+Context.batch_select = _batch_select
+Context.batch_pair_list = _batch_pair_list
+Context.batch_clear = _batch_clear
+Context.eval_binary = _eval_binary

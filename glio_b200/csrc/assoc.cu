@@ -360,15 +360,28 @@ __global__ void k_seg_counts(const SegDesc* __restrict__ segs, int nseg, const i
   if (s < nseg) counts[s] = pos[segs[s].offset + segs[s].count] - pos[segs[s].offset];
 }
 
-void compact_run(const AssocWork& w, const SegDesc* d_segs, int nseg, int* d_flags, int* d_pos, DevBuf<int>& scan_tmp,
-                 const void* d_dst /*CompactDst[nseg]*/, int* d_counts, cudaStream_t st, LaunchCounter& lc) {
+void compact_count(const AssocWork& w, const SegDesc* d_segs, int nseg, int* d_flags, int* d_pos, DevBuf<int>& scan_tmp,
+                   int* d_counts, cudaStream_t st, LaunchCounter& lc) {
   const int64_t Qt = w.Qt;
   const unsigned nb = (unsigned)((Qt + 1 + 255) / 256);
   lc.begin("k_flags", st); k_flags<<<nb, 256, 0, st>>>(w.status, Qt, d_flags); lc.end(st);
   exclusive_scan_i32(d_flags, d_pos, Qt + 1, scan_tmp, st, lc);
   lc.begin("k_seg_counts", st); k_seg_counts<<<(nseg + 127) / 128, 128, 0, st>>>(d_segs, nseg, d_pos, d_counts); lc.end(st);
+  GLIO_CUDA_TRY(cudaGetLastError());
+}
+
+void compact_scatter(const AssocWork& w, const SegDesc* d_segs, int nseg, const int* d_pos, const void* d_dst, cudaStream_t st,
+                     LaunchCounter& lc) {
+  const int64_t Qt = w.Qt;
+  const unsigned nb = (unsigned)((Qt + 255) / 256);
   lc.begin("k_compact", st); k_compact<<<nb, 256, 0, st>>>(d_segs, Qt, w.seg, w.status, d_pos, w.nsd, w.weight, w.normal_cent, (const CompactDst*)d_dst); lc.end(st);
   GLIO_CUDA_TRY(cudaGetLastError());
+}
+
+void compact_run(const AssocWork& w, const SegDesc* d_segs, int nseg, int* d_flags, int* d_pos, DevBuf<int>& scan_tmp,
+                 const void* d_dst /*CompactDst[nseg]*/, int* d_counts, cudaStream_t st, LaunchCounter& lc) {
+  compact_count(w, d_segs, nseg, d_flags, d_pos, scan_tmp, d_counts, st, lc);
+  compact_scatter(w, d_segs, nseg, d_pos, d_dst, st, lc);
 }
 
 // gather (feature selection as an input index list)

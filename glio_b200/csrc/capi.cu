@@ -51,6 +51,27 @@ struct glio_ctx {
 
   std::vector<std::unique_ptr<Slot>> slots;
 
+  // ---- batch (scan-to-multiscan) state
+  struct Frame {
+    int64_t Q = 0; int stride = 3;
+    DevBuf<float> scan; const float* scan_ptr = nullptr;
+    double pose[7] = {0, 0, 0, 1, 0, 0, 0};
+    GridBuild grid; bool grid_valid = false;
+  };
+  struct Pair {
+    int cur = 0, oth = 0;
+    DevBuf<float4> m_cpw; DevBuf<double> m_nc; DevBuf<int32_t> m_src; int64_t n_match = 0;
+    DevBuf<float4> s_cpw; DevBuf<double> s_nc; int64_t n_sel = -1;
+  };
+  std::map<int, std::unique_ptr<Frame>> frames;
+  std::vector<std::unique_ptr<Pair>> pairs;
+  std::map<std::pair<int, int>, int> pair_index;
+  bool bin_dirty = true; int bin_K = -1; int n_bin_items = 0;
+  glio_allreduce_fn allreduce = nullptr; void* allreduce_user = nullptr;
+  DevBuf<BinItem> d_bin_items; DevBuf<int> d_pair_item_start, d_kf_inc_start; DevBuf<BinIncidence> d_inc;
+  DevBuf<double> d_bin_partials, d_pair_sums, d_bin_diag, d_bin_off, d_bin_poses;
+  PinnedBuf<double> h_bin_diag, h_bin_off, h_bin_poses;
+
   // association workspace
   DevBuf<float4> w_pm, w_nsd;
   DevBuf<uint16_t> w_seg;
@@ -230,6 +251,26 @@ EvalParams eval_params(const glio_ctx* c) {
   return ep;
 }
 
+void fill_summary(const SolverSummary& S, int n, glio_solver_summary* summary, glio_iteration* iter_log, int iter_cap, double* step_log, int64_t step_cap) {
+  if (summary) {
+      memset(summary, 0, sizeof(*summary));
+      summary->termination = S.termination; summary->num_iterations = (int)S.iterations.size();
+      summary->num_successful_steps = S.num_successful_steps; summary->num_unsuccessful_steps = S.num_unsuccessful_steps;
+      summary->num_evaluations = S.num_evaluations; summary->num_jacobian_evaluations = S.num_jacobian_evaluations;
+      summary->num_linear_solves = S.num_linear_solves; summary->num_valid_steps = (int)(S.steps.size() / (size_t)n);
+      summary->initial_cost = S.initial_cost; summary->final_cost = S.final_cost;
+      snprintf(summary->message, sizeof(summary->message), "%s", S.message.c_str());
+    }
+    if (iter_log) for (int i = 0; i < (int)S.iterations.size() && i < iter_cap; ++i) {
+      const IterationRecord& r = S.iterations[i];
+      glio_iteration& q = iter_log[i];
+      q.iteration = r.iteration; q.step_is_valid = r.step_is_valid; q.step_is_successful = r.step_is_successful; q.reserved = 0;
+      q.cost = r.cost; q.cost_change = r.cost_change; q.gradient_max_norm = r.gradient_max_norm; q.gradient_norm = r.gradient_norm;
+      q.step_norm = r.step_norm; q.relative_decrease = r.relative_decrease; q.trust_region_radius = r.trust_region_radius; q.mu = r.mu;
+    }
+    if (step_log) memcpy(step_log, S.steps.data(), sizeof(double) * (size_t)std::min<int64_t>(step_cap, (int64_t)S.steps.size()));
+}
+
 // device evaluation of all active unary residuals -> c->h_out (W x 28: 21 upper-tri H, 6 g, 1 cost), synchronised
 void eval_unary_blocks(glio_ctx* c, int W, const double* poses_body, int jac_kind, bool want_jac) {
   build_items(c, W);
@@ -280,6 +321,10 @@ void glio_destroy(glio_ctx* c) {
   cudaSetDevice(c->device);
   if (c->st) cudaStreamSynchronize(c->st);
   c->map.release(); c->map_stage.release();
+  for (auto& f : c->frames) { f.second->scan.release(); f.second->grid.release(); }
+  for (auto& p : c->pairs) { p->m_cpw.release(); p->m_nc.release(); p->m_src.release(); p->s_cpw.release(); p->s_nc.release(); }
+  c->d_bin_items.release(); c->d_pair_item_start.release(); c->d_kf_inc_start.release(); c->d_inc.release(); c->d_bin_partials.release();
+  c->d_pair_sums.release(); c->d_bin_diag.release(); c->d_bin_off.release(); c->d_bin_poses.release(); c->h_bin_diag.release(); c->h_bin_off.release(); c->h_bin_poses.release();
   for (auto& s : c->slots) if (s) s->release();
   c->w_pm.release(); c->w_nsd.release(); c->w_seg.release(); c->w_order.release(); c->w_status.release(); c->w_weight.release();
   c->w_nc.release(); c->w_plane.release(); c->w_idx5.release(); c->w_sqd5.release(); c->w_flags.release(); c->w_pos.release();
@@ -530,27 +575,40 @@ int glio_window_solve(glio_ctx* c, int W, double* poses, double* speed_bias, gli
       for (int i = 0; i < 7; ++i) x[(size_t)na * k + i] = poses[7 * k + i];
       if (sb) for (int i = 0; i < 9; ++i) x[(size_t)na * k + 7 + i] = speed_bias[9 * k + i];
     }
-    EvalFn eval = [&](const double* xa, bool want_jac, double* cost, double* H, double* g) -> bool {
+    std::vector<double> Hd;       // dense scratch for the host callback's n x n interface
+    int hb_fixed = -1;
+    EvalFn eval = [&](const double* xa, bool want_jac, double* cost, BandMat* H, double* g) -> bool {
       for (int k = 0; k < W; ++k) {
         for (int i = 0; i < 7; ++i) pz[7 * k + i] = xa[(size_t)na * k + i];
         if (sb) for (int i = 0; i < 9; ++i) sz[9 * k + i] = xa[(size_t)na * k + 7 + i];
       }
       eval_unary_blocks(c, W, pz.data(), 0, want_jac);
       double ct = 0;
-      if (want_jac) { std::fill(H, H + (size_t)n * n, 0.0); std::fill(g, g + n, 0.0); }
-      for (int k = 0; k < W; ++k) {
-        const double* ob = c->h_out.p + (size_t)k * GLIO_NACC;
-        ct += ob[27];
-        if (want_jac) {
-          int idx = 0;
-          for (int p = 0; p < 6; ++p) for (int q = p; q < 6; ++q) {
-            H[(size_t)(nt * k + p) * n + nt * k + q] = ob[idx]; H[(size_t)(nt * k + q) * n + nt * k + p] = ob[idx]; ++idx;
-          }
-          for (int p = 0; p < 6; ++p) g[nt * k + p] = ob[21 + p];
-        }
+      for (int k = 0; k < W; ++k) ct += c->h_out.p[(size_t)k * GLIO_NACC + 27];
+      if (want_jac) {
+        std::fill(g, g + n, 0.0);
+        for (int k = 0; k < W; ++k) for (int p = 0; p < 6; ++p) g[nt * k + p] = c->h_out.p[(size_t)k * GLIO_NACC + 21 + p];
       }
       if (host_factors) {
-        if (host_factors(user, W, pz.data(), sb ? sz.data() : nullptr, want_jac ? 1 : 0, H, g, &ct) != 0) return false;
+        if (want_jac) Hd.assign((size_t)n * n, 0.0);
+        if (host_factors(user, W, pz.data(), sb ? sz.data() : nullptr, want_jac ? 1 : 0, want_jac ? Hd.data() : nullptr, g, &ct) != 0) return false;
+      }
+      if (want_jac) {
+        if (hb_fixed < 0) {
+          // the block structure of the problem is fixed, so the band of J^T J is too (window: prior + IMU chain + unary
+          // LiDAR blocks -> block tridiagonal); a dense coupling simply yields hb = n-1
+          int w = 5;
+          if (host_factors) for (int i = 0; i < n; ++i) for (int j = 0; j < i - w; ++j) if (Hd[(size_t)i * n + j] != 0.0 || Hd[(size_t)j * n + i] != 0.0) { w = i - j; break; }
+          hb_fixed = w;
+        }
+        H->reset(n, hb_fixed);
+        const int hb = H->hb;
+        if (host_factors) for (int i = 0; i < n; ++i) for (int j = std::max(0, i - hb); j <= i; ++j) H->at(i, j) = Hd[(size_t)i * n + j];
+        for (int k = 0; k < W; ++k) {
+          const double* ob = c->h_out.p + (size_t)k * GLIO_NACC;
+          int idx = 0;
+          for (int p = 0; p < 6; ++p) for (int q = p; q < 6; ++q) { H->at(nt * k + q, nt * k + p) += ob[idx]; ++idx; }
+        }
       }
       *cost = ct;
       return std::isfinite(ct);
@@ -561,24 +619,7 @@ int glio_window_solve(glio_ctx* c, int W, double* poses, double* speed_bias, gli
       for (int i = 0; i < 7; ++i) poses[7 * k + i] = x[(size_t)na * k + i];
       if (sb) for (int i = 0; i < 9; ++i) speed_bias[9 * k + i] = x[(size_t)na * k + 7 + i];
     }
-    if (summary) {
-      memset(summary, 0, sizeof(*summary));
-      summary->termination = S.termination; summary->num_iterations = (int)S.iterations.size();
-      summary->num_successful_steps = S.num_successful_steps; summary->num_unsuccessful_steps = S.num_unsuccessful_steps;
-      summary->num_evaluations = S.num_evaluations; summary->num_jacobian_evaluations = S.num_jacobian_evaluations;
-      summary->num_linear_solves = S.num_linear_solves; summary->num_valid_steps = (int)(S.steps.size() / (size_t)n);
-      summary->initial_cost = S.initial_cost; summary->final_cost = S.final_cost;
-      snprintf(summary->message, sizeof(summary->message), "%s", S.message.c_str());
-    }
-    if (iter_log) for (int i = 0; i < (int)S.iterations.size() && i < iter_cap; ++i) {
-      const IterationRecord& r = S.iterations[i];
-      glio_iteration& q = iter_log[i];
-      q.iteration = r.iteration; q.step_is_valid = r.step_is_valid; q.step_is_successful = r.step_is_successful; q.reserved = 0;
-      q.cost = r.cost; q.cost_change = r.cost_change; q.gradient_max_norm = r.gradient_max_norm; q.gradient_norm = r.gradient_norm;
-      q.step_norm = r.step_norm; q.relative_decrease = r.relative_decrease; q.trust_region_radius = r.trust_region_radius; q.mu = r.mu;
-    }
-    if (step_log) memcpy(step_log, S.steps.data(), sizeof(double) * (size_t)std::min<int64_t>(step_cap, (int64_t)S.steps.size()));
-    GLIO_REQUIRE(S.termination != TERM_FAILURE || true, GLIO_ERR_NUMERIC, S.message);
+    fill_summary(S, n, summary, iter_log, iter_cap, step_log, step_cap);
   });
 }
 
@@ -599,6 +640,344 @@ int glio_eval_unary_residuals(glio_ctx* c, int slot, const double pose_body[7], 
     if (r) GLIO_CUDA_TRY(cudaMemcpyAsync(r, c->d_r.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     if (J) GLIO_CUDA_TRY(cudaMemcpyAsync(J, c->d_J.p, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
     GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+  });
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// batch path: frames, pair association (K1b), binary evaluation (K2b)
+// ------------------------------------------------------------------------------------------------------------
+int glio_batch_clear(glio_ctx* c) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    for (auto& f : c->frames) { f.second->scan.release(); f.second->grid.release(); }
+    for (auto& p : c->pairs) { p->m_cpw.release(); p->m_nc.release(); p->m_src.release(); p->s_cpw.release(); p->s_nc.release(); }
+    c->frames.clear(); c->pairs.clear(); c->pair_index.clear(); c->bin_dirty = true;
+  });
+}
+
+int glio_batch_set_frame(glio_ctx* c, int frame, const float* scan_xyz, int64_t Q, int stride, int mem, const double pose[7]) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(frame >= 0 && pose, GLIO_ERR_ARG, "bad frame arguments");
+    auto& fp = c->frames[frame];
+    if (!fp) fp.reset(new glio_ctx::Frame());
+    glio_ctx::Frame& f = *fp;
+    f.scan_ptr = stage_points(c, f.scan, scan_xyz, Q, stride, mem);
+    f.Q = Q; f.stride = stride; f.grid_valid = false;
+    for (int i = 0; i < 7; ++i) f.pose[i] = pose[i];
+  });
+}
+
+// pose-only update (association always uses the poses registered here — the reference uses pose_info_keyframe, quirk Q8)
+int glio_batch_set_pose(glio_ctx* c, int frame, const double pose[7]) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    auto it = c->frames.find(frame);
+    GLIO_REQUIRE(it != c->frames.end() && pose, GLIO_ERR_ARG, "unknown frame");
+    for (int i = 0; i < 7; ++i) it->second->pose[i] = pose[i];
+    it->second->grid_valid = false;
+  });
+}
+
+int glio_batch_associate_pairs(glio_ctx* c, const int32_t* pairs_cur, const int32_t* pairs_oth, int64_t n_pairs, int64_t* n_match) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(n_pairs > 0 && pairs_cur && pairs_oth, GLIO_ERR_ARG, "bad pair list");
+    // group the requested pairs by the searched frame: one grid, one launch per group
+    std::map<int, std::vector<int64_t>> by_oth;
+    for (int64_t i = 0; i < n_pairs; ++i) {
+      GLIO_REQUIRE(c->frames.count(pairs_cur[i]) && c->frames.count(pairs_oth[i]) && pairs_cur[i] != pairs_oth[i], GLIO_ERR_ARG, "pair references an unknown frame");
+      by_oth[pairs_oth[i]].push_back(i);
+    }
+    AssocGates gates{c->prm.batch_max_radius, c->prm.batch_dist_thres, c->prm.weight_min};
+    for (auto& grp : by_oth) {
+      glio_ctx::Frame& fo = *c->frames[grp.first];
+      if (!fo.grid_valid) {
+        // world cloud of the searched frame (body pose applied directly to the stored points, quirk Q7) + its grid
+        grid_build(fo.grid, fo.scan_ptr, fo.stride, fo.Q, fo.pose, fo.pose + 3, c->prm.cell_size, c->pts_per_cell, c->st, c->lc);
+        fo.grid_valid = true;
+      }
+      const int nseg = (int)grp.second.size();
+      std::vector<SegDesc> segs(nseg);
+      int64_t Qt = 0;
+      for (int s = 0; s < nseg; ++s) {
+        glio_ctx::Frame& fc = *c->frames[pairs_cur[grp.second[s]]];
+        segs[s].src = fc.scan_ptr; segs[s].stride = fc.stride; segs[s].count = fc.Q; segs[s].offset = Qt;
+        for (int k = 0; k < 3; ++k) segs[s].t[k] = fc.pose[k];
+        for (int k = 0; k < 4; ++k) segs[s].q[k] = fc.pose[3 + k];
+        Qt += fc.Q;
+      }
+      ensure_work(c, Qt, true);
+      c->d_segs.reserve(nseg); c->d_dst.reserve(nseg); c->d_counts.reserve(nseg); c->h_counts.reserve(nseg);
+      GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_segs.p, segs.data(), nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, c->st));
+      AssocWork w = make_work(c, Qt, true);
+      assoc_run(fo.grid, c->d_segs.p, nseg, w, gates, fo.scan_ptr, fo.stride, c->cell_count, c->cell_pos, c->scan_tmp, c->st, c->lc);
+      compact_count(w, c->d_segs.p, nseg, c->w_flags.p, c->w_pos.p, c->scan_tmp, c->d_counts.p, c->st, c->lc);
+      GLIO_CUDA_TRY(cudaMemcpyAsync(c->h_counts.p, c->d_counts.p, nseg * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+      GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+      std::vector<CompactDst> dst(nseg);
+      for (int s = 0; s < nseg; ++s) {
+        const int64_t i = grp.second[s];
+        const std::pair<int, int> key(pairs_cur[i], pairs_oth[i]);
+        auto pit = c->pair_index.find(key);
+        int pi;
+        if (pit == c->pair_index.end()) { pi = (int)c->pairs.size(); c->pairs.emplace_back(new glio_ctx::Pair()); c->pair_index[key] = pi; }
+        else pi = pit->second;
+        glio_ctx::Pair& pr = *c->pairs[pi];
+        pr.cur = key.first; pr.oth = key.second; pr.n_match = c->h_counts.p[s]; pr.n_sel = -1;
+        const size_t nm = (size_t)std::max<int64_t>(pr.n_match, 1);
+        pr.m_cpw.reserve(nm); pr.m_nc.reserve(6 * nm); pr.m_src.reserve(nm);
+        dst[s].cpw = pr.m_cpw.p; dst[s].nsd = nullptr; dst[s].nc = pr.m_nc.p; dst[s].src = pr.m_src.p;
+        if (n_match) n_match[i] = pr.n_match;
+      }
+      GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_dst.p, dst.data(), nseg * sizeof(CompactDst), cudaMemcpyHostToDevice, c->st));
+      compact_scatter(w, c->d_segs.p, nseg, c->w_pos.p, c->d_dst.p, c->st, c->lc);
+      GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));   // dst/segs are stack vectors
+    }
+    c->bin_dirty = true;
+  });
+}
+
+int glio_batch_associate(glio_ctx* c, int cur, const int32_t* oth, int n_oth, int64_t* n_match) {
+  if (!c || !oth || n_oth <= 0) return GLIO_ERR_ARG;
+  std::vector<int32_t> cc(n_oth, cur);
+  return glio_batch_associate_pairs(c, cc.data(), oth, n_oth, n_match);
+}
+
+int glio_batch_pair_list(glio_ctx* c, int64_t capacity, int32_t* cur, int32_t* oth, int64_t* n_pairs) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    const int64_t n = (int64_t)c->pairs.size();
+    if (n_pairs) *n_pairs = n;
+    GLIO_REQUIRE(capacity >= n || (!cur && !oth), GLIO_ERR_ARG, "capacity smaller than the pair count");
+    for (int64_t i = 0; i < n; ++i) { if (cur) cur[i] = c->pairs[i]->cur; if (oth) oth[i] = c->pairs[i]->oth; }
+  });
+}
+
+int glio_batch_get_matches(glio_ctx* c, int cur, int oth, int64_t capacity, float* cp, float* weight, double* normal_cent, int32_t* src, int64_t* n_out) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    auto it = c->pair_index.find(std::make_pair(cur, oth));
+    GLIO_REQUIRE(it != c->pair_index.end(), GLIO_ERR_ARG, "pair was not associated");
+    glio_ctx::Pair& pr = *c->pairs[it->second];
+    const int64_t n = pr.n_match;
+    if (n_out) *n_out = n;
+    GLIO_REQUIRE(capacity >= n, GLIO_ERR_ARG, "capacity smaller than the match count");
+    if (n == 0) return;
+    std::vector<float4> h;
+    if (cp || weight) { h.resize(n); GLIO_CUDA_TRY(cudaMemcpyAsync(h.data(), pr.m_cpw.p, n * sizeof(float4), cudaMemcpyDeviceToHost, c->st)); }
+    if (normal_cent) GLIO_CUDA_TRY(cudaMemcpyAsync(normal_cent, pr.m_nc.p, 6 * n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    if (src) GLIO_CUDA_TRY(cudaMemcpyAsync(src, pr.m_src.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    for (int64_t i = 0; i < n && !h.empty(); ++i) {
+      if (cp) { cp[3 * i] = h[i].x; cp[3 * i + 1] = h[i].y; cp[3 * i + 2] = h[i].z; }
+      if (weight) weight[i] = h[i].w;
+    }
+  });
+}
+
+int glio_batch_select(glio_ctx* c, int cur, int oth, const int32_t* keep, int64_t n) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    auto it = c->pair_index.find(std::make_pair(cur, oth));
+    GLIO_REQUIRE(it != c->pair_index.end(), GLIO_ERR_ARG, "pair was not associated");
+    glio_ctx::Pair& pr = *c->pairs[it->second];
+    c->bin_dirty = true;
+    if (n < 0) { pr.n_sel = -1; return; }
+    GLIO_REQUIRE(n == 0 || keep, GLIO_ERR_ARG, "null selection list");
+    pr.n_sel = n;
+    if (n == 0) return;
+    c->d_keep.reserve(n); c->d_bad.reserve(1); pr.s_cpw.reserve(n); pr.s_nc.reserve(6 * n);
+    GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_keep.p, keep, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->st));
+    GLIO_CUDA_TRY(cudaMemsetAsync(c->d_bad.p, 0, sizeof(int), c->st));
+    gather_selection(c->d_keep.p, n, pr.n_match, pr.m_cpw.p, nullptr, pr.m_nc.p, pr.s_cpw.p, nullptr, pr.s_nc.p, c->d_bad.p, c->st, c->lc);
+    int bad = 0;
+    GLIO_CUDA_TRY(cudaMemcpyAsync(&bad, c->d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    if (bad) { pr.n_sel = -1; throw Error{GLIO_ERR_ARG, "selection index out of range"}; }
+  });
+}
+
+}  // extern "C"
+
+namespace {
+
+// work items + incidence lists of the binary evaluation (rebuilt when associations / selections change)
+void build_bin_items(glio_ctx* c, int K) {
+  if (!c->bin_dirty && c->bin_K == K) return;
+  const int P = (int)c->pairs.size();
+  std::vector<BinItem> items;
+  std::vector<int> pstart(P + 1, 0);
+  std::vector<std::vector<BinIncidence>> inc(K);
+  for (int p = 0; p < P; ++p) {
+    glio_ctx::Pair& pr = *c->pairs[p];
+    GLIO_REQUIRE(pr.cur < K && pr.oth < K, GLIO_ERR_ARG, "pair references a keyframe >= K");
+    pstart[p] = (int)items.size();
+    const bool sel = pr.n_sel >= 0;
+    const int64_t n = sel ? pr.n_sel : pr.n_match;
+    const float4* cpw = sel ? pr.s_cpw.p : pr.m_cpw.p;
+    const double* nc = sel ? pr.s_nc.p : pr.m_nc.p;
+    for (int64_t o = 0; o < n; o += GLIO_ITEM_MAX) {
+      BinItem it; it.cpw = cpw + o; it.nc = nc + 6 * o; it.count = (int32_t)std::min<int64_t>(GLIO_ITEM_MAX, n - o); it.kf_c = pr.cur; it.kf_o = pr.oth;
+      items.push_back(it);
+    }
+    inc[pr.cur].push_back(BinIncidence{p, 0});
+    inc[pr.oth].push_back(BinIncidence{p, 1});
+  }
+  pstart[P] = (int)items.size();
+  std::vector<int> kstart(K + 1, 0);
+  std::vector<BinIncidence> flat;
+  for (int k = 0; k < K; ++k) { kstart[k] = (int)flat.size(); flat.insert(flat.end(), inc[k].begin(), inc[k].end()); }
+  kstart[K] = (int)flat.size();
+  c->n_bin_items = (int)items.size();
+  c->d_bin_items.reserve(items.size() + 1); c->d_pair_item_start.reserve(P + 1); c->d_kf_inc_start.reserve(K + 1); c->d_inc.reserve(flat.size() + 1);
+  c->d_bin_partials.reserve((items.size() + 1) * GLIO_NACC_BIN); c->d_pair_sums.reserve((size_t)(P + 1) * GLIO_NACC_BIN);
+  c->d_bin_diag.reserve((size_t)K * GLIO_NACC); c->d_bin_off.reserve((size_t)(P + 1) * 36); c->d_bin_poses.reserve((size_t)K * 7);
+  c->h_bin_diag.reserve((size_t)K * GLIO_NACC); c->h_bin_off.reserve((size_t)(P + 1) * 36); c->h_bin_poses.reserve((size_t)K * 7);
+  if (!items.empty()) GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_bin_items.p, items.data(), items.size() * sizeof(BinItem), cudaMemcpyHostToDevice, c->st));
+  GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_pair_item_start.p, pstart.data(), (P + 1) * sizeof(int), cudaMemcpyHostToDevice, c->st));
+  GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_kf_inc_start.p, kstart.data(), (K + 1) * sizeof(int), cudaMemcpyHostToDevice, c->st));
+  if (!flat.empty()) GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_inc.p, flat.data(), flat.size() * sizeof(BinIncidence), cudaMemcpyHostToDevice, c->st));
+  GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+  c->bin_dirty = false; c->bin_K = K;
+}
+
+// device evaluation of all active binary residuals -> c->h_bin_diag (K x 28), c->h_bin_off (P x 36), synchronised
+void eval_binary_blocks(glio_ctx* c, int K, const double* poses, bool want_jac, double huber) {
+  build_bin_items(c, K);
+  const int P = (int)c->pairs.size();
+  memcpy(c->h_bin_poses.p, poses, (size_t)K * 7 * sizeof(double));
+  GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_bin_poses.p, c->h_bin_poses.p, (size_t)K * 7 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  eval_binary_run(c->d_bin_items.p, c->n_bin_items, c->d_pair_item_start.p, P, K, c->d_bin_poses.p, c->prm.batch_score, huber, want_jac,
+                  c->d_bin_partials.p, c->d_pair_sums.p, c->d_kf_inc_start.p, c->d_inc.p, c->d_bin_diag.p, c->d_bin_off.p, nullptr, c->st, c->lc);
+  if (c->allreduce) {
+    // keyframe-sharded evaluation: every rank holds the same pair list but only its own pairs carry residuals;
+    // one sum over ranks of the pose-block buffers per evaluation (SURVEY 8e "pose-block allreduce")
+    GLIO_REQUIRE(c->allreduce(c->allreduce_user, c->d_bin_diag.p, (int64_t)K * GLIO_NACC, (void*)c->st) == 0, GLIO_ERR_NCCL, "allreduce hook failed (diag)");
+    if (want_jac && P > 0)
+      GLIO_REQUIRE(c->allreduce(c->allreduce_user, c->d_bin_off.p, (int64_t)P * 36, (void*)c->st) == 0, GLIO_ERR_NCCL, "allreduce hook failed (off)");
+  }
+  GLIO_CUDA_TRY(cudaMemcpyAsync(c->h_bin_diag.p, c->d_bin_diag.p, (size_t)K * GLIO_NACC * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  if (want_jac && P > 0) GLIO_CUDA_TRY(cudaMemcpyAsync(c->h_bin_off.p, c->d_bin_off.p, (size_t)P * 36 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+}
+
+}  // namespace
+
+extern "C" {
+
+int glio_eval_binary(glio_ctx* c, int K, const double* poses, double* Hdiag, double* Hoff, double* g, double* cost) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(K > 0 && poses, GLIO_ERR_ARG, "bad arguments");
+    const bool want_jac = Hdiag || Hoff || g;
+    eval_binary_blocks(c, K, poses, want_jac, /*no loss on batch LiDAR factors, Estimator.cpp:2768*/ 0.0);
+    double ct = 0;
+    for (int k = 0; k < K; ++k) {
+      const double* o = c->h_bin_diag.p + (size_t)k * GLIO_NACC;
+      if (Hdiag) { int idx = 0; for (int p = 0; p < 6; ++p) for (int q = p; q < 6; ++q) { Hdiag[36 * k + 6 * p + q] = o[idx]; Hdiag[36 * k + 6 * q + p] = o[idx]; ++idx; } }
+      if (g) for (int p = 0; p < 6; ++p) g[6 * k + p] = o[21 + p];
+      ct += o[27];
+    }
+    if (Hoff) memcpy(Hoff, c->h_bin_off.p, c->pairs.size() * 36 * sizeof(double));
+    if (cost) *cost = ct;
+  });
+}
+
+
+int glio_set_allreduce(glio_ctx* c, glio_allreduce_fn fn, void* user) {
+  if (!c) return GLIO_ERR_ARG;
+  c->allreduce = fn; c->allreduce_user = user;
+  return GLIO_OK;
+}
+
+int glio_batch_declare_pairs(glio_ctx* c, const int32_t* pairs_cur, const int32_t* pairs_oth, int64_t n_pairs) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    for (int64_t i = 0; i < n_pairs; ++i) {
+      const std::pair<int, int> key(pairs_cur[i], pairs_oth[i]);
+      if (c->pair_index.count(key)) continue;
+      c->pair_index[key] = (int)c->pairs.size();
+      c->pairs.emplace_back(new glio_ctx::Pair());
+      c->pairs.back()->cur = key.first; c->pairs.back()->oth = key.second;
+    }
+    c->bin_dirty = true;
+  });
+}
+
+int glio_batch_solve(glio_ctx* c, int K, double* poses, double* speed_bias, glio_host_factors_band_fn host_factors, void* user,
+                     const glio_solver_options* options, glio_solver_summary* summary, glio_iteration* iter_log, int iter_cap,
+                     double* step_log, int64_t step_cap) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(K > 0 && poses, GLIO_ERR_ARG, "bad arguments");
+    glio_solver_options o;
+    if (options) o = *options;
+    else { glio_default_solver_options(&o); o.dogleg_type = 1; o.use_nonmonotonic_steps = 1; o.max_num_iterations = 100; }  // Estimator.cpp:3276-3281
+    const bool sb = speed_bias != nullptr;
+    const int nt = sb ? 15 : 6, na = sb ? 16 : 7, n = K * nt;
+    int span = 1;
+    for (auto& p : c->pairs) span = std::max(span, std::abs(p->cur - p->oth));
+    const int hb = (span + 1) * nt - 1;
+    std::vector<ParamBlock> blocks;
+    for (int k = 0; k < K; ++k) {
+      blocks.push_back(ParamBlock{na * k, 3, nt * k, 3, false});
+      blocks.push_back(ParamBlock{na * k + 3, 4, nt * k + 3, 3, true});
+      if (sb) blocks.push_back(ParamBlock{na * k + 7, 9, nt * k + 6, 9, false});
+    }
+    SolverOptions so;
+    so.max_num_iterations = o.max_num_iterations; so.dogleg_type = o.dogleg_type; so.use_nonmonotonic_steps = o.use_nonmonotonic_steps != 0;
+    so.max_consecutive_nonmonotonic_steps = o.max_consecutive_nonmonotonic_steps;
+    so.initial_trust_region_radius = o.initial_trust_region_radius; so.max_trust_region_radius = o.max_trust_region_radius;
+    so.min_trust_region_radius = o.min_trust_region_radius; so.min_relative_decrease = o.min_relative_decrease;
+    so.min_lm_diagonal = o.min_lm_diagonal; so.max_lm_diagonal = o.max_lm_diagonal;
+    so.max_num_consecutive_invalid_steps = o.max_num_consecutive_invalid_steps; so.jacobi_scaling = o.jacobi_scaling != 0;
+    so.function_tolerance = o.function_tolerance; so.gradient_tolerance = o.gradient_tolerance; so.parameter_tolerance = o.parameter_tolerance;
+    so.fuse_candidate_jacobian = o.fuse_candidate_jacobian != 0;
+    TrustRegionDogleg solver(blocks, so);
+    std::vector<double> x((size_t)K * na), pz((size_t)K * 7), sz((size_t)K * 9);
+    for (int k = 0; k < K; ++k) {
+      for (int i = 0; i < 7; ++i) x[(size_t)na * k + i] = poses[7 * k + i];
+      if (sb) for (int i = 0; i < 9; ++i) x[(size_t)na * k + 7 + i] = speed_bias[9 * k + i];
+    }
+    EvalFn eval = [&](const double* xa, bool want_jac, double* cost, BandMat* H, double* g) -> bool {
+      for (int k = 0; k < K; ++k) {
+        for (int i = 0; i < 7; ++i) pz[7 * k + i] = xa[(size_t)na * k + i];
+        if (sb) for (int i = 0; i < 9; ++i) sz[9 * k + i] = xa[(size_t)na * k + 7 + i];
+      }
+      eval_binary_blocks(c, K, pz.data(), want_jac, 0.0);
+      double ct = 0;
+      for (int k = 0; k < K; ++k) ct += c->h_bin_diag.p[(size_t)k * GLIO_NACC + 27];
+      if (want_jac) {
+        H->reset(n, hb);
+        std::fill(g, g + n, 0.0);
+        for (int k = 0; k < K; ++k) {
+          const double* ob = c->h_bin_diag.p + (size_t)k * GLIO_NACC;
+          int idx = 0;
+          for (int p = 0; p < 6; ++p) for (int q = p; q < 6; ++q) { H->at(nt * k + q, nt * k + p) += ob[idx]; ++idx; }
+          for (int p = 0; p < 6; ++p) g[nt * k + p] = ob[21 + p];
+        }
+        for (size_t pi = 0; pi < c->pairs.size(); ++pi) {
+          const int kc = c->pairs[pi]->cur, ko = c->pairs[pi]->oth;
+          const double* ob = c->h_bin_off.p + pi * 36;
+          for (int p = 0; p < 6; ++p) for (int q = 0; q < 6; ++q) H->add_sym(nt * kc + p, nt * ko + q, ob[6 * p + q]);
+        }
+      }
+      if (host_factors) {
+        if (host_factors(user, K, pz.data(), sb ? sz.data() : nullptr, want_jac ? 1 : 0, want_jac ? H->a.data() : nullptr, want_jac ? H->hb : 0, g, &ct) != 0) return false;
+      }
+      *cost = ct;
+      return std::isfinite(ct);
+    };
+    SolverSummary S;
+    solver.solve(x.data(), eval, &S);
+    for (int k = 0; k < K; ++k) {
+      for (int i = 0; i < 7; ++i) poses[7 * k + i] = x[(size_t)na * k + i];
+      if (sb) for (int i = 0; i < 9; ++i) speed_bias[9 * k + i] = x[(size_t)na * k + 7 + i];
+    }
+    fill_summary(S, n, summary, iter_log, iter_cap, step_log, step_cap);
   });
 }
 

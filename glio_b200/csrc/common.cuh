@@ -174,6 +174,10 @@ void exclusive_scan_i32(const int* in, int* out, int64_t n, DevBuf<int>& tmp, cu
 void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const AssocWork& w, const AssocGates& gates,
                const float* oth_local, int oth_stride, DevBuf<int>& cell_count, DevBuf<int>& cell_pos,
                DevBuf<int>& scan_tmp, cudaStream_t st, LaunchCounter& lc);
+void compact_count(const AssocWork& w, const SegDesc* d_segs, int nseg, int* d_flags, int* d_pos, DevBuf<int>& scan_tmp,
+                   int* d_counts, cudaStream_t st, LaunchCounter& lc);
+void compact_scatter(const AssocWork& w, const SegDesc* d_segs, int nseg, const int* d_pos, const void* d_dst, cudaStream_t st,
+                     LaunchCounter& lc);
 void compact_run(const AssocWork& w, const SegDesc* d_segs, int nseg, int* d_flags, int* d_pos, DevBuf<int>& scan_tmp,
                  const void* d_dst /*CompactDst[nseg]*/, int* d_counts, cudaStream_t st, LaunchCounter& lc);
 void gather_selection(const int32_t* d_keep, int64_t n, int64_t n_match, const float4* cpw, const float4* nsd, const double* nc,
@@ -192,5 +196,21 @@ void eval_unary_run(const EvalItem* d_items, int nitems, int W, const double* d_
                     cudaStream_t st, LaunchCounter& lc);
 void eval_unary_residuals_run(const float4* cpw, const float4* nsd, int64_t n, const double* d_pose, const EvalParams& ep,
                               int jac_kind, double* d_r, double* d_J, cudaStream_t st, LaunchCounter& lc);
+
+
+// ---- K2b (eval.cu): binary plane factors
+struct BinItem {
+  const float4* cpw;          // (cp.xyz, weight)
+  const double* nc;           // 6 per residual: local-frame unit normal, local-frame centroid
+  int32_t count;
+  int32_t kf_c, kf_o;
+};
+constexpr int GLIO_NACC_BIN = 55;   // uu(6) uv(9) vv(6) uz(9) vz(9) zz(6) | r*u(3) r*v(3) r*z(3) | cost
+// incidence list of a keyframe for the deterministic block assembly: (pair index, role 0 = cur / 1 = oth)
+struct BinIncidence { int32_t pair; int32_t role; };
+void eval_binary_run(const BinItem* d_items, int nitems, const int* d_pair_item_start, int n_pairs, int K, const double* d_poses,
+                     double score_scale, double huber_delta, bool want_jac, double* d_partials, double* d_pair_sums,
+                     const int* d_kf_inc_start, const BinIncidence* d_inc, double* d_diag /*K*28*/, double* d_off /*n_pairs*36*/,
+                     double* d_cost, cudaStream_t st, LaunchCounter& lc);
 
 }  // namespace glio

@@ -237,4 +237,173 @@ void eval_unary_residuals_run(const float4* cpw, const float4* nsd, int64_t n, c
   GLIO_CUDA_TRY(cudaGetLastError());
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2b: binary (scan-to-multiscan) plane factors, BinaryLidarPlaneNormFactor (LidarKeyframeFactor.h:124-164):
+//   p_w = R(q_c) cp + t_c ;  N = R(q_o) n_l ;  c_w = R(q_o) c_l + t_o ;  r = s N.(p_w - c_w),  s = batch_score * weight
+// tangent Jacobians:  J_c = [u | v],  J_o = [-u | z]  with  u = s N,  v = 2 s (R(q_c)cp x N),  z = 2 s (N x (p_w - t_o)).
+// Because J_o's translation part is -u, the 12x12 outer product needs only 45 distinct sums (+9 for J^T r, +1 cost).
+// HBM traffic per residual: 16 B (cp, weight) + 48 B (n_l, c_l as the reference stores them: double) = 64 B.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int NB = GLIO_NACC_BIN;
+constexpr int BIN_T = 128;
+
+struct PairFrame { double R1[9], t1[3], R2[9], t2[3]; };
+
+template <bool WANT_JAC>
+__global__ void __launch_bounds__(BIN_T) k_eval_binary(const BinItem* __restrict__ items, const double* __restrict__ poses, double score_scale,
+                                                       double huber_delta, double* __restrict__ partials) {
+  __shared__ PairFrame F;
+  __shared__ double red[BIN_T / 32][NB];
+  const BinItem it = items[blockIdx.x];
+  if (threadIdx.x == 0) {
+    const double* P1 = poses + 7 * it.kf_c; const double* P2 = poses + 7 * it.kf_o;
+    double q1[4] = {P1[3], P1[4], P1[5], P1[6]}, q2[4] = {P2[3], P2[4], P2[5], P2[6]};
+    quat_to_mat(q1, F.R1); quat_to_mat(q2, F.R2);
+    F.t1[0] = P1[0]; F.t1[1] = P1[1]; F.t1[2] = P1[2]; F.t2[0] = P2[0]; F.t2[1] = P2[1]; F.t2[2] = P2[2];
+  }
+  __syncthreads();
+  double acc[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) acc[k] = 0.0;
+  for (int i = threadIdx.x; i < it.count; i += BIN_T) {
+    const float4 c4 = __ldg(&it.cpw[i]);
+    const double2* ncp = reinterpret_cast<const double2*>(it.nc + 6 * (int64_t)i);
+    const double2 n01 = __ldg(ncp), n2c0 = __ldg(ncp + 1), c12 = __ldg(ncp + 2);
+    const double s = score_scale * (double)c4.w;
+    double a1[3]; mat_vec3(F.R1, (double)c4.x, (double)c4.y, (double)c4.z, a1);
+    const double pw[3] = {a1[0] + F.t1[0], a1[1] + F.t1[1], a1[2] + F.t1[2]};
+    double N[3]; mat_vec3(F.R2, n01.x, n01.y, n2c0.x, N);
+    double co[3]; mat_vec3(F.R2, n2c0.y, c12.x, c12.y, co);
+    const double pm[3] = {pw[0] - F.t2[0], pw[1] - F.t2[1], pw[2] - F.t2[2]};     // p_w - t_o
+    const double dd[3] = {pm[0] - co[0], pm[1] - co[1], pm[2] - co[2]};           // p_w - c_w
+    double r = s * (N[0] * dd[0] + N[1] * dd[1] + N[2] * dd[2]);
+    double scale;
+    acc[54] += huber_scale(r, huber_delta, scale);
+    if (WANT_JAC) {
+      const double ss = s * scale;
+      const double u[3] = {ss * N[0], ss * N[1], ss * N[2]};
+      const double v[3] = {2.0 * ss * (a1[1] * N[2] - a1[2] * N[1]), 2.0 * ss * (a1[2] * N[0] - a1[0] * N[2]), 2.0 * ss * (a1[0] * N[1] - a1[1] * N[0])};
+      const double z[3] = {2.0 * ss * (N[1] * pm[2] - N[2] * pm[1]), 2.0 * ss * (N[2] * pm[0] - N[0] * pm[2]), 2.0 * ss * (N[0] * pm[1] - N[1] * pm[0])};
+      r *= scale;
+      int k = 0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b) acc[k++] += u[a] * u[b];          // uu  [0,6)
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) acc[k++] += u[a] * v[b];          // uv  [6,15)
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b) acc[k++] += v[a] * v[b];          // vv  [15,21)
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) acc[k++] += u[a] * z[b];          // uz  [21,30)
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) acc[k++] += v[a] * z[b];          // vz  [30,39)
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b) acc[k++] += z[a] * z[b];          // zz  [39,45)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) { acc[45 + a] += r * u[a]; acc[48 + a] += r * v[a]; acc[51 + a] += r * z[a]; }
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = WANT_JAC ? 0 : 54; k < NB; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NB) {
+    double v = 0.0;
+    if (WANT_JAC || threadIdx.x == 54) {
+#pragma unroll
+      for (int w4 = 0; w4 < BIN_T / 32; ++w4) v += red[w4][threadIdx.x];
+    }
+    partials[(size_t)blockIdx.x * NB + threadIdx.x] = v;
+  }
+}
+
+// per pair: sum of its items' partials, in item order (deterministic)
+__global__ void __launch_bounds__(64) k_bin_pair_sums(const double* __restrict__ partials, const int* __restrict__ pair_item_start,
+                                                      double* __restrict__ pair_sums) {
+  const int p = blockIdx.x, k = threadIdx.x;
+  if (k >= NB) return;
+  double v = 0.0;
+  for (int b = pair_item_start[p]; b < pair_item_start[p + 1]; ++b) v += partials[(size_t)b * NB + k];
+  pair_sums[(size_t)p * NB + k] = v;
+}
+
+__device__ __forceinline__ int sym3(int a, int b) { return a <= b ? (a * 3 - a * (a - 1) / 2 + (b - a)) : (b * 3 - b * (b - 1) / 2 + (a - b)); }
+
+// block assembly: blocks [0,K) -> diagonal 6x6 (21 upper-tri) + g (6) + per-KF cost share (cost is attributed to cur);
+// blocks [K, K+n_pairs) -> off-diagonal 6x6 (row = cur tangent, col = oth tangent)
+__global__ void __launch_bounds__(64) k_bin_assemble(const double* __restrict__ S, int K, int n_pairs, const int* __restrict__ kf_inc_start,
+                                                     const BinIncidence* __restrict__ inc, const int* __restrict__ pair_kf /*2 per pair*/,
+                                                     double* __restrict__ diag, double* __restrict__ off) {
+  const int b = blockIdx.x, e = threadIdx.x;
+  if (b < K) {
+    if (e >= GLIO_NACC) return;
+    double v = 0.0;
+    // decode entry e: [0,21) upper-tri (p<=q) of the 6x6, [21,27) g, 27 cost
+    int p = 0, q = 0;
+    if (e < 21) { int k = e; for (p = 0; p < 6; ++p) { if (k < 6 - p) { q = p + k; break; } k -= 6 - p; } }
+    for (int i = kf_inc_start[b]; i < kf_inc_start[b + 1]; ++i) {
+      const double* s = S + (size_t)inc[i].pair * NB;
+      const int role = inc[i].role;
+      if (e < 21) {
+        if (p < 3 && q < 3) v += s[sym3(p, q)];                                         // uu (both roles)
+        else if (p < 3) v += role == 0 ? s[6 + 3 * p + (q - 3)] : -s[21 + 3 * p + (q - 3)];   // uv | -uz
+        else v += role == 0 ? s[15 + sym3(p - 3, q - 3)] : s[39 + sym3(p - 3, q - 3)];  // vv | zz
+      } else if (e < 27) {
+        const int c = e - 21;
+        if (c < 3) v += role == 0 ? s[45 + c] : -s[45 + c];                              // r u | -r u
+        else v += role == 0 ? s[48 + (c - 3)] : s[51 + (c - 3)];                         // r v | r z
+      } else if (role == 0) v += s[54];
+    }
+    diag[(size_t)b * GLIO_NACC + e] = v;
+  } else {
+    const int pr = b - K;
+    if (pr >= n_pairs || e >= 36) return;
+    const double* s = S + (size_t)pr * NB;
+    const int p = e / 6, q = e % 6;
+    double v;
+    if (p < 3 && q < 3) v = -s[sym3(p, q)];                 // -u u^T
+    else if (p < 3) v = s[21 + 3 * p + (q - 3)];            //  u z^T
+    else if (q < 3) v = -s[6 + 3 * q + (p - 3)];            // -v u^T
+    else v = s[30 + 3 * (p - 3) + (q - 3)];                 //  v z^T
+    off[(size_t)pr * 36 + e] = v;
+  }
+}
+
+void eval_binary_run(const BinItem* d_items, int nitems, const int* d_pair_item_start, int n_pairs, int K, const double* d_poses,
+                     double score_scale, double huber_delta, bool want_jac, double* d_partials, double* d_pair_sums,
+                     const int* d_kf_inc_start, const BinIncidence* d_inc, double* d_diag, double* d_off, double* d_cost,
+                     cudaStream_t st, LaunchCounter& lc) {
+  (void)d_cost;
+  if (nitems > 0) {
+    lc.begin(want_jac ? "k_eval_binary" : "k_eval_binary_cost", st);
+    if (want_jac) k_eval_binary<true><<<nitems, BIN_T, 0, st>>>(d_items, d_poses, score_scale, huber_delta, d_partials);
+    else k_eval_binary<false><<<nitems, BIN_T, 0, st>>>(d_items, d_poses, score_scale, huber_delta, d_partials);
+    lc.end(st);
+  }
+  if (n_pairs > 0) {
+    lc.begin("k_bin_pair_sums", st); k_bin_pair_sums<<<n_pairs, 64, 0, st>>>(d_partials, d_pair_item_start, d_pair_sums); lc.end(st);
+  }
+  lc.begin("k_bin_assemble", st);
+  k_bin_assemble<<<K + (want_jac ? n_pairs : 0), 64, 0, st>>>(d_pair_sums, K, n_pairs, d_kf_inc_start, d_inc, nullptr, d_diag, d_off);
+  lc.end(st);
+  GLIO_CUDA_TRY(cudaGetLastError());
+}
+
 }  // namespace glio

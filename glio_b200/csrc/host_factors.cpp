@@ -34,9 +34,14 @@ inline void At_skew(const double A[9], const double v[3], double s, double M[9])
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double a = 0; for (int k = 0; k < 3; ++k) a += A[3 * k + i] * S[3 * k + j]; M[3 * i + j] = s * a; }
 }
 
+struct DenseAdder { double* H; int n; inline void operator()(int i, int j, double v) const { H[(size_t)i * n + j] += v; } };
+// lower-band storage (solver.h BandMat): only i >= j is stored
+struct BandAdder { double* a; int hb; inline void operator()(int i, int j, double v) const { if (i >= j && i - j <= hb) a[(size_t)i * (hb + 1) + (j - i + hb)] += v; } };
+
 // accumulate an m-row factor with dense tangent Jacobian blocks into H, g
+template <class Adder>
 inline void accumulate(int m, const double* r, int nb, const int* off, const int* width, const double* const* J /*m x width[b]*/,
-                       int n, double* H, double* g) {
+                       const Adder& add, double* g) {
   for (int a = 0; a < nb; ++a) {
     for (int p = 0; p < width[a]; ++p) {
       double gp = 0;
@@ -45,7 +50,7 @@ inline void accumulate(int m, const double* r, int nb, const int* off, const int
       for (int b = 0; b < nb; ++b) for (int q = 0; q < width[b]; ++q) {
         double h = 0;
         for (int k = 0; k < m; ++k) h += J[a][k * width[a] + p] * J[b][k * width[b] + q];
-        H[(size_t)(off[a] + p) * n + off[b] + q] += h;
+        add(off[a] + p, off[b] + q, h);
       }
     }
   }
@@ -86,11 +91,14 @@ void glio_hf_add_range(glio_host_factor_set* s, int kf, const double lever[3], c
   s->ranges.push_back(f);
 }
 
-// glio_host_factors_fn-compatible evaluation (user = glio_host_factor_set*)
-int glio_hf_evaluate(void* user, int W, const double* poses, const double* speed_bias, int want_jac, double* H, double* g, double* cost) {
+}  // extern "C"
+
+template <class Adder>
+static int hf_evaluate_impl(void* user, int W, const double* poses, const double* speed_bias, int want_jac, const Adder& add, double* g, double* cost) {
   const glio_host_factor_set& S = *(const glio_host_factor_set*)user;
   const bool sb = speed_bias != nullptr;
-  const int nt = sb ? 15 : 6, n = W * nt;
+  const int nt = sb ? 15 : 6;
+  (void)W;
   double c = 0;
   for (const Prior& f : S.priors) {
     const double* t = poses + 7 * f.kf; const double* q = t + 3;
@@ -111,7 +119,7 @@ int glio_hf_evaluate(void* user, int W, const double* poses, const double* speed
       }
       if (sb) for (int k = 0; k < 9; ++k) J[(size_t)(6 + k) * nt + 6 + k] = f.sw[6 + k];
       const int off[1] = {nt * f.kf}, width[1] = {nt}; const double* Jp[1] = {J.data()};
-      accumulate(15, r, 1, off, width, Jp, n, H, g);
+      accumulate(15, r, 1, off, width, Jp, add, g);
     }
   }
   for (const Between& f : S.betweens) {
@@ -158,7 +166,7 @@ int glio_hf_evaluate(void* user, int W, const double* poses, const double* speed
       }
       if (sb) for (int k = 0; k < 6; ++k) { Ji[(size_t)(9 + k) * nt + 9 + k] = -f.sw[9 + k]; Jj[(size_t)(9 + k) * nt + 9 + k] = f.sw[9 + k]; }
       const int off[2] = {nt * f.i, nt * f.j}, width[2] = {nt, nt}; const double* Jp[2] = {Ji.data(), Jj.data()};
-      accumulate(15, r, 2, off, width, Jp, n, H, g);
+      accumulate(15, r, 2, off, width, Jp, add, g);
     }
   }
   for (const Range& f : S.ranges) {
@@ -173,11 +181,23 @@ int glio_hf_evaluate(void* user, int W, const double* poses, const double* speed
       double cr[3]; glio::h_cross3(a, ph, cr);
       double J[6] = {f.w * ph[0], f.w * ph[1], f.w * ph[2], 2.0 * f.w * cr[0], 2.0 * f.w * cr[1], 2.0 * f.w * cr[2]};
       const int off[1] = {nt * f.kf}, width[1] = {6}; const double* Jp[1] = {J};
-      accumulate(1, r, 1, off, width, Jp, n, H, g);
+      accumulate(1, r, 1, off, width, Jp, add, g);
     }
   }
   *cost += c;
   return 0;
+}
+
+extern "C" {
+
+// glio_host_factors_fn-compatible evaluation (user = glio_host_factor_set*): dense n x n H
+int glio_hf_evaluate(void* user, int W, const double* poses, const double* speed_bias, int want_jac, double* H, double* g, double* cost) {
+  const int n = W * (speed_bias ? 15 : 6);
+  return hf_evaluate_impl(user, W, poses, speed_bias, want_jac, DenseAdder{H, n}, g, cost);
+}
+// glio_host_factors_band_fn-compatible evaluation: lower-band storage (batch problems)
+int glio_hf_evaluate_band(void* user, int K, const double* poses, const double* speed_bias, int want_jac, double* Hband, int hb, double* g, double* cost) {
+  return hf_evaluate_impl(user, K, poses, speed_bias, want_jac, BandAdder{Hband, hb}, g, cost);
 }
 
 }  // extern "C"

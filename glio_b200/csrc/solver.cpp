@@ -66,11 +66,15 @@ namespace {
 
 inline double dot(const std::vector<double>& a, const std::vector<double>& b) { double s = 0; for (size_t i = 0; i < a.size(); ++i) s += a[i] * b[i]; return s; }
 inline double norm(const std::vector<double>& a) { return std::sqrt(dot(a, a)); }
-// y = A x for symmetric dense A
-inline void symv(const std::vector<double>& A, int n, int hb, const std::vector<double>& x, std::vector<double>& y) {
+// y = A x for a symmetric matrix in lower-band storage
+inline void symv(const BandMat& A, const std::vector<double>& x, std::vector<double>& y) {
+  const int n = A.n, hb = A.hb, w = hb + 1;
+  for (int i = 0; i < n; ++i) y[i] = 0.0;
   for (int i = 0; i < n; ++i) {
-    const int j0 = hb < 0 ? 0 : std::max(0, i - hb), j1 = hb < 0 ? n : std::min(n, i + hb + 1);
-    double s = 0; const double* r = &A[(size_t)i * n]; for (int j = j0; j < j1; ++j) s += r[j] * x[j]; y[i] = s;
+    const double* ri = A.a.data() + (size_t)i * w + hb - i;
+    double s = ri[i] * x[i];
+    for (int j = std::max(0, i - hb); j < i; ++j) { s += ri[j] * x[j]; y[j] += ri[j] * x[i]; }
+    y[i] += s;
   }
 }
 
@@ -99,7 +103,8 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
   SolverSummary& S = *sum;
   S = SolverSummary();
   std::vector<double> x(x_io, x_io + na), cand(na), proj(na);
-  std::vector<double> H((size_t)n * n), g(n), Hs((size_t)n * n), gs(n), Hc((size_t)n * n), gc(n), A((size_t)n * n);
+  BandMat H, Hs, Hc, A;
+  std::vector<double> g(n), gs(n), gc(n);
   std::vector<double> scale(n, 1.0), diag(n), grad_d(n), gn(n), step(n), delta(n), tmp(n), tmp2(n), y(n), negg(n);
   double x_cost = 0, cand_cost = 0, minimum_cost = std::numeric_limits<double>::max(), model_cost_change = 0;
   double x_norm = -1;  // trust_region_minimizer.cc:175 "Invalid value"
@@ -112,12 +117,12 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
   double sub_B[4] = {0, 0, 0, 0}, sub_g[2] = {0, 0};
   bool sub_1d = false;
 
-  int hb = opt_.half_bandwidth;   // half bandwidth of H (detected from the sparsity pattern at iteration 0 when < 0)
   auto apply_scaling = [&]() {
+    Hs.n = H.n; Hs.hb = H.hb; Hs.a.resize(H.a.size());
+    const int hb = H.hb, w = hb + 1;
     for (int i = 0; i < n; ++i) {
       const double si = scale[i];
-      const int j0 = hb < 0 ? 0 : std::max(0, i - hb), j1 = hb < 0 ? n : std::min(n, i + hb + 1);
-      for (int j = j0; j < j1; ++j) Hs[(size_t)i * n + j] = H[(size_t)i * n + j] * si * scale[j];
+      for (int j = std::max(0, i - hb); j <= i; ++j) Hs.a[(size_t)i * w + (j - i + hb)] = H.a[(size_t)i * w + (j - i + hb)] * si * scale[j];
       gs[i] = g[i] * si;
     }
   };
@@ -215,7 +220,7 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
     sub_g[0] = dot(basis0, grad_d); sub_g[1] = dot(basis1, grad_d);
     for (int i = 0; i < n; ++i) { tmp[i] = basis0[i] / diag[i]; tmp2[i] = basis1[i] / diag[i]; }
     std::vector<double> h0(n), h1(n);
-    symv(Hs, n, hb, tmp, h0); symv(Hs, n, hb, tmp2, h1);
+    symv(Hs, tmp, h0); symv(Hs, tmp2, h1);
     sub_B[0] = dot(tmp, h0); sub_B[1] = dot(tmp, h1); sub_B[2] = sub_B[1]; sub_B[3] = dot(tmp2, h1);
     return true;
   };
@@ -223,18 +228,18 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
   auto compute_step = [&]() -> int {
     if (reuse) { if (opt_.dogleg_type == 0) traditional(); else subspace(); return 0; }
     reuse = true;
-    for (int i = 0; i < n; ++i) diag[i] = std::sqrt(std::min(std::max(Hs[(size_t)i * n + i], opt_.min_lm_diagonal), opt_.max_lm_diagonal));
+    for (int i = 0; i < n; ++i) diag[i] = std::sqrt(std::min(std::max(Hs.at(i, i), opt_.min_lm_diagonal), opt_.max_lm_diagonal));
     for (int i = 0; i < n; ++i) grad_d[i] = gs[i] / diag[i];
     for (int i = 0; i < n; ++i) tmp[i] = grad_d[i] / diag[i];
-    symv(Hs, n, hb, tmp, tmp2);
+    symv(Hs, tmp, tmp2);
     alpha = dot(grad_d, grad_d) / dot(tmp, tmp2);
     bool ok = false;
     while (mu < max_mu) {
       A = Hs;
       const double sm = std::sqrt(mu);
-      for (int i = 0; i < n; ++i) { const double lm = diag[i] * sm; A[(size_t)i * n + i] += lm * lm; }
+      for (int i = 0; i < n; ++i) { const double lm = diag[i] * sm; A.at(i, i) += lm * lm; }
       S.num_linear_solves++;
-      if (detail::cholesky_solve(A, n, hb, gs.data(), y.data())) { ok = true; break; }
+      if (detail::cholesky_solve(A, gs.data(), y.data())) { ok = true; break; }
       mu *= mu_inc;
     }
     if (!ok) return 1;
@@ -248,18 +253,11 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
   IterationRecord it{};
   it.iteration = 0;
   S.num_evaluations++; S.num_jacobian_evaluations++;
-  if (!eval(x.data(), true, &x_cost, H.data(), g.data())) {
+  if (!eval(x.data(), true, &x_cost, &H, g.data()) || H.n != n) {
     S.termination = TERM_FAILURE; S.message = "Residual and Jacobian evaluation failed."; return;
   }
   S.initial_cost = x_cost; S.final_cost = x_cost;
-  if (hb < 0) {
-    // the block structure of the problem is fixed, so the band of J^T J is too: factor only inside it
-    // (window: prior + IMU chain + unary LiDAR blocks -> block tridiagonal; a dense coupling simply yields hb = n-1)
-    int w = 0;
-    for (int i = 0; i < n; ++i) for (int j = 0; j < i - w; ++j) if (H[(size_t)i * n + j] != 0.0 || H[(size_t)j * n + i] != 0.0) { w = i - j; break; }
-    hb = w;
-  }
-  if (opt_.jacobi_scaling) for (int i = 0; i < n; ++i) scale[i] = 1.0 / (1.0 + std::sqrt(H[(size_t)i * n + i]));
+  if (opt_.jacobi_scaling) for (int i = 0; i < n; ++i) scale[i] = 1.0 / (1.0 + std::sqrt(H.at(i, i)));
   apply_scaling();
   it.cost = x_cost; gradient_norms(it);
   it.step_is_valid = 1; it.step_is_successful = 1;
@@ -286,7 +284,7 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
     const int rc = compute_step();
     bool valid = false;
     if (rc == 0) {
-      symv(Hs, n, hb, step, tmp);
+      symv(Hs, step, tmp);
       model_cost_change = -(dot(step, gs) + 0.5 * dot(step, tmp));
       valid = model_cost_change > 0.0;
       if (valid) { for (int i = 0; i < n; ++i) delta[i] = step[i] * scale[i]; num_consecutive_invalid = 0; }
@@ -306,7 +304,7 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
     plus(x.data(), delta.data(), cand.data());
     const bool fused = opt_.fuse_candidate_jacobian;
     S.num_evaluations++; if (fused) S.num_jacobian_evaluations++;
-    if (!eval(cand.data(), fused, &cand_cost, fused ? Hc.data() : nullptr, fused ? gc.data() : nullptr))
+    if (!eval(cand.data(), fused, &cand_cost, fused ? &Hc : nullptr, fused ? gc.data() : nullptr))
       cand_cost = std::numeric_limits<double>::max();
     // ParameterToleranceReached (:676-693)
     { double s2 = 0; for (int i = 0; i < na; ++i) { const double d = x[i] - cand[i]; s2 += d * d; } it.step_norm = std::sqrt(s2); }
@@ -324,10 +322,10 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
       // HandleSuccessfulStep (:757-771)
       x = cand;
       { double s2 = 0; for (int i = 0; i < na; ++i) s2 += x[i] * x[i]; x_norm = std::sqrt(s2); }
-      if (fused) { H.swap(Hc); g.swap(gc); x_cost = cand_cost; }
+      if (fused) { std::swap(H, Hc); g.swap(gc); x_cost = cand_cost; }
       else {
         S.num_evaluations++; S.num_jacobian_evaluations++;
-        if (!eval(x.data(), true, &x_cost, H.data(), g.data())) { S.termination = TERM_FAILURE; S.message = "Residual and Jacobian evaluation failed."; return; }
+        if (!eval(x.data(), true, &x_cost, &H, g.data())) { S.termination = TERM_FAILURE; S.message = "Residual and Jacobian evaluation failed."; return; }
       }
       apply_scaling();
       it.cost = x_cost; gradient_norms(it);

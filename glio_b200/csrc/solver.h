@@ -43,7 +43,6 @@ struct SolverOptions {
   double gradient_tolerance = 1e-10;
   double parameter_tolerance = 1e-8;
   bool jacobi_scaling = true;
-  int half_bandwidth = -1;   // >= 0: H is banded with this many sub-diagonals (batch); -1: dense
   bool fuse_candidate_jacobian = true;  // evaluate J together with the candidate cost, reuse on acceptance
 };
 
@@ -65,8 +64,22 @@ struct SolverSummary {
   int num_evaluations = 0, num_jacobian_evaluations = 0, num_linear_solves = 0;
 };
 
-// evaluate(x_ambient, want_jac, &cost, H (n*n row-major, overwritten, full symmetric), g (n, overwritten)) -> ok
-using EvalFn = std::function<bool(const double*, bool, double*, double*, double*)>;
+// Symmetric matrix in lower-band storage: entry (i,j), i-hb <= j <= i, lives at a[i*(hb+1) + (j-i+hb)].
+// hb = n-1 is a dense lower triangle.  The block structure of the problems here is fixed, so the band is too:
+// window = block tridiagonal (prior + IMU chain + unary LiDAR), batch = (2*search_range+1) block band.
+struct BandMat {
+  int n = 0, hb = 0;
+  std::vector<double> a;
+  void reset(int n_, int hb_) { n = n_; hb = std::min(hb_, std::max(n_ - 1, 0)); a.assign((size_t)n * (hb + 1), 0.0); }
+  inline double& at(int i, int j) { return a[(size_t)i * (hb + 1) + (j - i + hb)]; }          // requires i-hb <= j <= i
+  inline double at(int i, int j) const { return a[(size_t)i * (hb + 1) + (j - i + hb)]; }
+  inline double sym(int i, int j) const { return i >= j ? (i - j <= hb ? at(i, j) : 0.0) : (j - i <= hb ? at(j, i) : 0.0); }
+  inline void add_sym(int i, int j, double v) { if (i >= j) at(i, j) += v; else at(j, i) += v; }   // one triangle only
+};
+
+// evaluate(x_ambient, want_jac, &cost, H, g) -> ok.  When want_jac the evaluator calls H->reset(n, hb) itself (the band
+// it needs; it must be the same on every call) and fills the lower band + g (n, overwritten).
+using EvalFn = std::function<bool(const double*, bool, double*, BandMat*, double*)>;
 
 namespace detail {
 
@@ -85,34 +98,39 @@ inline void quat_plus(const double* x, const double* d, double* o) {
   }
 }
 
-// Cholesky of a symmetric positive definite matrix stored dense row-major (lower part used), optional band.
+// In-place band Cholesky A = L L^T (lower band storage) and solve L L^T x = b.
 // Returns false if a pivot is not positive / finite (Ceres: LINEAR_SOLVER_FAILURE -> mu escalation).
-inline bool cholesky_solve(std::vector<double>& A, int n, int hb, const double* b, double* x) {
-  auto lo = [&](int i) { return hb < 0 ? 0 : std::max(0, i - hb); };
+inline bool cholesky_solve(BandMat& A, const double* b, double* x) {
+  const int n = A.n, hb = A.hb, w = hb + 1;
+  double* a = A.a.data();
   for (int j = 0; j < n; ++j) {
-    double d = A[(size_t)j * n + j];
-    for (int k = lo(j); k < j; ++k) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+    double* rj = a + (size_t)j * w + hb - j;          // rj[k] == A(j,k)
+    const int kj0 = std::max(0, j - hb);
+    double d = rj[j];
+    for (int k = kj0; k < j; ++k) d -= rj[k] * rj[k];
     if (!(d > 0.0) || !std::isfinite(d)) return false;
     const double ljj = std::sqrt(d);
-    A[(size_t)j * n + j] = ljj;
-    const int imax = hb < 0 ? n : std::min(n, j + hb + 1);
+    rj[j] = ljj;
+    const int imax = std::min(n, j + hb + 1);
     for (int i = j + 1; i < imax; ++i) {
-      double s = A[(size_t)i * n + j];
-      const int k0 = std::max(lo(i), lo(j));
-      for (int k = k0; k < j; ++k) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
-      A[(size_t)i * n + j] = s / ljj;
+      double* ri = a + (size_t)i * w + hb - i;
+      const int k0 = std::max(kj0, i - hb);
+      double s = ri[j];
+      for (int k = k0; k < j; ++k) s -= ri[k] * rj[k];
+      ri[j] = s / ljj;
     }
   }
   for (int i = 0; i < n; ++i) {
+    const double* ri = a + (size_t)i * w + hb - i;
     double s = b[i];
-    for (int k = lo(i); k < i; ++k) s -= A[(size_t)i * n + k] * x[k];
-    x[i] = s / A[(size_t)i * n + i];
+    for (int k = std::max(0, i - hb); k < i; ++k) s -= ri[k] * x[k];
+    x[i] = s / ri[i];
   }
   for (int i = n - 1; i >= 0; --i) {
     double s = x[i];
-    const int kmax = hb < 0 ? n : std::min(n, i + hb + 1);
-    for (int k = i + 1; k < kmax; ++k) s -= A[(size_t)k * n + i] * x[k];
-    x[i] = s / A[(size_t)i * n + i];
+    const int kmax = std::min(n, i + hb + 1);
+    for (int k = i + 1; k < kmax; ++k) s -= a[(size_t)k * w + hb - k + i] * x[k];
+    x[i] = s / a[(size_t)i * w + hb];
   }
   for (int i = 0; i < n; ++i) if (!std::isfinite(x[i])) return false;
   return true;

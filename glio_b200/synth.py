@@ -1,7 +1,7 @@
 """Seeded synthetic workloads for the LiDAR hot path (SURVEY.md §8(d) "Synthetic inputs").
 
-Street-canyon scene in a world frame whose origin is >= 5 m from every surface (avoids the
-n·x = -1 singularity of the reference plane model, quirk Q2): ground z = -1.8, walls y = ±12,
+Street-canyon scene in a world frame with no surface through the origin (avoids the n·x = -1
+singularity of the reference plane model, quirk Q2): ground z = -1.8, walls y = ±12,
 cross walls every 40 m in x (offset so none passes through x = 0), random boxes.  Points are sampled
 uniformly by area + N(0, 0.02 m) along the surface normal + U(-1e-3, 1e-3) jitter (kills kNN distance
 ties).  All coordinates are float32, as the reference's pcl::PointXYZI clouds are.
@@ -162,11 +162,11 @@ def window_problem(W=20, Q=100_000, M=1_000_000, seed=SEED0 + 2, n_boxes=30):
                 t_lb=T_LB.copy(), W=W, Q=Q, M=M, seed=seed)
 
 
-def batch_problem(K=200, Q=100_000, seed=SEED0 + 3, search_range=6):
+def batch_problem(K=200, Q=100_000, seed=SEED0 + 3, search_range=6, rng_range=50.0):
     """cfg 3 / cfg 4 style batch problem: K keyframes, scans in the body frame."""
     rng = np.random.default_rng(seed)
     scene = Scene(-60.0, K + 60.0, rng)
     truth = trajectory(K, rng)
     init = perturb(truth, rng, sig_t=0.03, sig_r_deg=0.2)
-    scans = [scan_in_body_frame(scene, truth[k], Q, rng) for k in range(K)]
+    scans = [scan_in_body_frame(scene, truth[k], Q, rng, rng_range) for k in range(K)]
     return dict(scans=scans, poses_true=truth, poses_init=init, K=K, Q=Q, search_range=search_range, seed=seed)

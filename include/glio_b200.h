@@ -199,37 +199,59 @@ void glio_hf_add_range(glio_host_factor_set* s, int kf, const double lever[3], c
 int glio_hf_evaluate(void* user, int W, const double* poses, const double* speed_bias, int want_jac, double* H, double* g, double* cost);
 
 /* ---- K1b: scan-to-multiscan (batch) association.
- * Replaces findGlobalCorrespondingSurfFeatures_Batch / ...Add_Batch (Estimator.cpp:3710-3892).
- * Frames are registered once; a pair (cur, oth) associates every point of frame cur against frame oth. */
+ * Replaces findGlobalCorrespondingSurfFeatures_Batch / ...Add_Batch (Estimator.cpp:3710-3892) and their driver
+ * batchFeatureAssociation (:3413-3432).  Frames (one keyframe's surf scan, stored as received + its pose from
+ * pose_info_keyframe, quirks Q7/Q8) are registered once; a pair (cur, oth) associates every point of frame `cur`
+ * against the world cloud of frame `oth`.  The uniform grid of a frame is built once and reused by every pair
+ * that searches it (the reference rebuilds a kd-tree per pair, Estimator.cpp:3729-3731: same neighbours). */
 int glio_batch_set_frame(glio_ctx* ctx, int frame, const float* scan_xyz, int64_t Q, int stride_floats, int mem,
                          const double pose[7]);
+int glio_batch_set_pose(glio_ctx* ctx, int frame, const double pose[7]);
 /* associate `cur` against each of oth[n_oth]; n_match[n_oth] receives gl_vec_surf_res_cnt[cur][oth]. */
 int glio_batch_associate(glio_ctx* ctx, int cur, const int32_t* oth, int n_oth, int64_t* n_match);
-/* all pairs at once: pairs_cur[n], pairs_oth[n] */
+/* many pairs at once (grouped by searched frame internally): pairs_cur[n], pairs_oth[n] */
 int glio_batch_associate_pairs(glio_ctx* ctx, const int32_t* pairs_cur, const int32_t* pairs_oth, int64_t n_pairs,
                                int64_t* n_match);
+/* matches of one pair: cp[3n] float (point of cur, local), weight[n] float (score = batch_score*weight),
+ * normal_cent[6n] double (unit normal and centroid of the 5 neighbours in oth's LOCAL frame), src[n] */
 int glio_batch_get_matches(glio_ctx* ctx, int cur, int oth, int64_t capacity, float* cp, float* weight,
-                           double* normal_cent /*6n*/, int32_t* src, int64_t* n_match);
+                           double* normal_cent, int32_t* src, int64_t* n_match);
+/* globalFeatureSelection_Batch (Estimator.cpp:3994-4116) as an input index list; n < 0 clears */
 int glio_batch_select(glio_ctx* ctx, int cur, int oth, const int32_t* keep, int64_t n);
+int glio_batch_pair_list(glio_ctx* ctx, int64_t capacity, int32_t* cur, int32_t* oth, int64_t* n_pairs);
 int glio_batch_clear(glio_ctx* ctx);
 
-/* ---- K2b: evaluate all active binary plane residuals.
- * Replaces ResidualBlock::Evaluate over BinaryLidarPlaneNormFactor (LidarKeyframeFactor.h:124-164).
- *   poses[K*7]; outputs in block-banded form: Hdiag[K*36], Hoff[n_pairs*36] (block (cur,oth), row = cur
- *   tangent, col = oth tangent, in the order pairs were associated; query with glio_batch_pair_list),
- *   g[K*6], cost (scalar). */
+/* Creates (empty) pair entries in the given order without associating them: on a keyframe-sharded multi-GPU run
+ * every rank declares the SAME global pair list and then associates only the pairs it owns, so the block
+ * buffers have one layout everywhere. */
+int glio_batch_declare_pairs(glio_ctx* ctx, const int32_t* pairs_cur, const int32_t* pairs_oth, int64_t n_pairs);
+
+/* ---- K2b: evaluate all active binary plane residuals at poses[K*7].
+ * Replaces ResidualBlock::Evaluate over BinaryLidarPlaneNormFactor (LidarKeyframeFactor.h:124-164; no loss function,
+ * Estimator.cpp:2768) and the J^T J / J^T r accumulation.  Block-sparse output: Hdiag[K*36], Hoff[n_pairs*36]
+ * (block (cur,oth): row = cur tangent, col = oth tangent, pairs in glio_batch_pair_list order), g[K*6], cost. */
 int glio_eval_binary(glio_ctx* ctx, int K, const double* poses, double* Hdiag, double* Hoff, double* g, double* cost);
-int glio_batch_pair_list(glio_ctx* ctx, int64_t capacity, int32_t* cur, int32_t* oth, int64_t* n_pairs);
 
-/* ---- K2e: edge residuals (LidarEdgeFactor, LidarKeyframeFactor.h:12-70 — defined but never instantiated
- * by the reference; evaluated here from caller-provided correspondences). */
-int glio_set_edges(glio_ctx* ctx, int slot, const float* cp, const float* pa, const float* pb, const double* s,
-                   int64_t n, int mem);
-int glio_eval_edge(glio_ctx* ctx, int W, const double* poses_body, double* H, double* g, double* cost);
+/* ---- batch minimizer (replaces ceres::Solve of optimizeBatchWithLandMark, Estimator.cpp:3275-3284: SUBSPACE_DOGLEG,
+ * nonmonotonic steps, max_num_iter iterations; options == NULL selects exactly those).  The normal equations are
+ * block-banded (half bandwidth (max|cur-oth|+1)*nt - 1) and stored/factored in band form.  Host factors (IMU chain,
+ * delta_q, DD pseudorange: host C++ by design) accumulate into the same LOWER-BAND storage:
+ * entry (i,j), i-hb <= j <= i, lives at Hband[i*(hb+1) + (j-i+hb)]. */
+typedef int (*glio_host_factors_band_fn)(void* user, int K, const double* poses, const double* speed_bias, int want_jac,
+                                         double* Hband, int hb, double* g, double* cost);
+int glio_hf_evaluate_band(void* user, int K, const double* poses, const double* speed_bias, int want_jac, double* Hband, int hb,
+                          double* g, double* cost);
+int glio_batch_solve(glio_ctx* ctx, int K, double* poses, double* speed_bias, glio_host_factors_band_fn host_factors, void* user,
+                     const glio_solver_options* options, glio_solver_summary* summary, glio_iteration* iter_log, int iter_cap,
+                     double* step_log, int64_t step_cap);
 
-/* ---- multi-GPU (batch path only): sum the block buffers over ranks with NCCL (SURVEY §8 e).
- * comm is an ncclComm_t as void*. */
-int glio_allreduce_blocks(glio_ctx* ctx, void* nccl_comm, double* d_buf, int64_t count);
+/* ---- multi-GPU (batch path only; the window path is "replicas only").
+ * Keyframe-sharded ranks sum their pose-block buffers once per evaluation.  The library does not link NCCL: the
+ * caller installs the reduction (in-place sum over ranks of count doubles at device pointer d_buf, enqueued on
+ * `cuda_stream`).  glio_b200/libglio_nccl.so provides glio_nccl_allreduce for an ncclComm_t; Python callers may
+ * install a torch.distributed-based hook instead. */
+typedef int (*glio_allreduce_fn)(void* user, double* d_buf, int64_t count, void* cuda_stream);
+int glio_set_allreduce(glio_ctx* ctx, glio_allreduce_fn fn, void* user);
 
 #ifdef __cplusplus
 }

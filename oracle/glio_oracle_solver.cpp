@@ -70,6 +70,8 @@ struct Problem {
   double q_lb[4], t_lb[3], huber, lidar_unused;
   // unary lidar
   std::vector<int32_t> kf; std::vector<float> cp, nsd; std::vector<double> score;
+  // binary lidar (batch)
+  std::vector<int32_t> bkc, bko; std::vector<float> bcp; std::vector<double> bnc, bscore;
   std::vector<Prior> priors; std::vector<Between> betweens; std::vector<Range> ranges;
   // CRS jacobian
   std::vector<double> r; std::vector<int64_t> rowptr; std::vector<int32_t> col; std::vector<double> val;
@@ -81,11 +83,12 @@ void quat_plus_jac(const double* x, double* P) { go_quat_plus_jacobian(x, P); }
 
 // number of rows / nnz layout is fixed for a problem: unary rows (6 nnz), prior rows 15 x nt, between 15 x 2nt, range 1 x 6
 void layout(Problem& P) {
-  const int64_t N = (int64_t)P.kf.size();
-  P.nrows = N + 15 * (int64_t)P.priors.size() + 15 * (int64_t)P.betweens.size() + (int64_t)P.ranges.size();
+  const int64_t N = (int64_t)P.kf.size(), NB = (int64_t)P.bkc.size();
+  P.nrows = N + NB + 15 * (int64_t)P.priors.size() + 15 * (int64_t)P.betweens.size() + (int64_t)P.ranges.size();
   P.rowptr.assign(P.nrows + 1, 0);
   int64_t row = 0, nnz = 0;
   for (int64_t i = 0; i < N; ++i) { P.rowptr[row++] = nnz; nnz += 6; }
+  for (int64_t i = 0; i < NB; ++i) { P.rowptr[row++] = nnz; nnz += 12; }
   for (size_t i = 0; i < P.priors.size(); ++i) for (int k = 0; k < 15; ++k) { P.rowptr[row++] = nnz; nnz += P.nt; }
   for (size_t i = 0; i < P.betweens.size(); ++i) for (int k = 0; k < 15; ++k) { P.rowptr[row++] = nnz; nnz += 2 * P.nt; }
   for (size_t i = 0; i < P.ranges.size(); ++i) { P.rowptr[row++] = nnz; nnz += 6; }
@@ -140,6 +143,25 @@ bool evaluate(Problem& P, const double* x, bool want_jac, double* cost_out) {
     for (int t = 0; t < T; ++t) cost += ct[t];
   }
   int64_t row = N;
+  // ---- binary LiDAR rows (BinaryLidarPlaneNormFactor, no loss: Estimator.cpp:2768) ----
+  {
+    const int64_t NB = (int64_t)P.bkc.size();
+    if (NB > 0) {
+      std::vector<double> poses((size_t)P.W * 7);
+      for (int k = 0; k < P.W; ++k) for (int i = 0; i < 7; ++i) poses[7 * k + i] = x[(size_t)P.na * k + i];
+      std::vector<double> Jt(want_jac ? (size_t)NB * 12 : 0);
+      double ct = 0;
+      go_eval_binary(P.mode, P.W, poses.data(), 0.0, NB, P.bkc.data(), P.bko.data(), P.bcp.data(), P.bnc.data(), P.bscore.data(),
+                     P.r.data() + row, want_jac ? Jt.data() : nullptr, nullptr, nullptr, nullptr, &ct);
+      cost += ct;
+      if (want_jac) for (int64_t i = 0; i < NB; ++i) {
+        int64_t p = P.rowptr[row + i];
+        for (int c = 0; c < 6; ++c) { P.col[p + c] = P.nt * P.bkc[i] + c; P.val[p + c] = Jt[(size_t)i * 12 + c]; }
+        for (int c = 0; c < 6; ++c) { P.col[p + 6 + c] = P.nt * P.bko[i] + c; P.val[p + 6 + c] = Jt[(size_t)i * 12 + 6 + c]; }
+      }
+      row += NB;
+    }
+  }
   // ---- prior rows ----
   for (const Prior& f : P.priors) {
     const double* xa = x + (size_t)P.na * f.kf;
@@ -256,6 +278,11 @@ void go_problem_add_unary(void* h, int64_t N, const int32_t* kf, const float* cp
   Problem* P = (Problem*)h;
   P->kf.insert(P->kf.end(), kf, kf + N); P->cp.insert(P->cp.end(), cp, cp + 3 * N); P->nsd.insert(P->nsd.end(), nsd, nsd + 4 * N); P->score.insert(P->score.end(), score, score + N);
 }
+void go_problem_add_binary(void* h, int64_t N, const int32_t* kf_c, const int32_t* kf_o, const float* cp, const double* nc, const double* score) {
+  Problem* P = (Problem*)h;
+  P->bkc.insert(P->bkc.end(), kf_c, kf_c + N); P->bko.insert(P->bko.end(), kf_o, kf_o + N); P->bcp.insert(P->bcp.end(), cp, cp + 3 * N);
+  P->bnc.insert(P->bnc.end(), nc, nc + 6 * N); P->bscore.insert(P->bscore.end(), score, score + N);
+}
 void go_problem_add_prior(void* h, int kf, const double t0[3], const double q0[4], const double* sb0, const double sw[15]) {
   Prior f; f.kf = kf; for (int i = 0; i < 3; ++i) f.t0[i] = t0[i]; for (int i = 0; i < 4; ++i) f.q0[i] = q0[i];
   for (int i = 0; i < 9; ++i) f.sb0[i] = sb0 ? sb0[i] : 0.0; for (int i = 0; i < 15; ++i) f.sw[i] = sw[i];
@@ -269,6 +296,10 @@ void go_problem_add_range(void* h, int kf, const double lever[3], const double s
   Range f; f.kf = kf; for (int k = 0; k < 3; ++k) { f.lever[k] = lever[k]; f.sat[k] = sat[k]; } f.rho = rho; f.w = w;
   ((Problem*)h)->ranges.push_back(f);
 }
+void go_problem_set_state(void* h, const double* poses, const double* speed_bias) {
+  Problem* P = (Problem*)h;
+  for (int k = 0; k < P->W; ++k) { for (int i = 0; i < 7; ++i) P->x[(size_t)P->na * k + i] = poses[7 * k + i]; if (P->has_sb && speed_bias) for (int i = 0; i < 9; ++i) P->x[(size_t)P->na * k + 7 + i] = speed_bias[9 * k + i]; }
+}
 void go_problem_get_state(void* h, double* poses, double* speed_bias) {
   Problem* P = (Problem*)h;
   for (int k = 0; k < P->W; ++k) { for (int i = 0; i < 7; ++i) poses[7 * k + i] = P->x[(size_t)P->na * k + i]; if (P->has_sb && speed_bias) for (int i = 0; i < 9; ++i) speed_bias[9 * k + i] = P->x[(size_t)P->na * k + 7 + i]; }
@@ -277,7 +308,7 @@ void go_problem_get_state(void* h, double* poses, double* speed_bias) {
 // product's analytic host factors): H[n*n], g[n], cost
 void go_problem_host_normal_eq(void* h, double* H, double* g, double* cost) {
   Problem* P = (Problem*)h;
-  Problem Q = *P; Q.kf.clear(); Q.cp.clear(); Q.nsd.clear(); Q.score.clear();
+  Problem Q = *P; Q.kf.clear(); Q.cp.clear(); Q.nsd.clear(); Q.score.clear(); Q.bkc.clear(); Q.bko.clear(); Q.bcp.clear(); Q.bnc.clear(); Q.bscore.clear();
   layout(Q); double c = 0; evaluate(Q, Q.x.data(), true, &c);
   const int n = Q.n; std::fill(H, H + (size_t)n * n, 0.0); std::fill(g, g + n, 0.0);
   for (int64_t i = 0; i < Q.nrows; ++i) for (int64_t p = Q.rowptr[i]; p < Q.rowptr[i + 1]; ++p) {

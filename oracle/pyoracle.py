@@ -241,6 +241,11 @@ class WindowProblem:
         kf = np.ascontiguousarray(kf, np.int32); cp = _f32(cp).reshape(-1, 3); nsd = _f32(nsd).reshape(-1, 4); score = _f64(score)
         lib().go_problem_add_unary(self.h, C.c_int64(len(kf)), _p(kf), _p(cp), _p(nsd), _p(score))
 
+    def add_binary(self, kf_c, kf_o, cp, normal_cent, score):
+        kf_c = np.ascontiguousarray(kf_c, np.int32); kf_o = np.ascontiguousarray(kf_o, np.int32)
+        cp = _f32(cp).reshape(-1, 3); nc = _f64(normal_cent).reshape(-1, 6); score = _f64(score)
+        lib().go_problem_add_binary(self.h, C.c_int64(len(kf_c)), _p(kf_c), _p(kf_o), _p(cp), _p(nc), _p(score))
+
     def add_prior(self, kf, t0, q0, sb0, sqrt_w):
         lib().go_problem_add_prior(self.h, C.c_int(kf), _p(_f64(t0)), _p(_f64(q0)), _p(None if sb0 is None else _f64(sb0)), _p(_f64(sqrt_w)))
 
@@ -249,6 +254,10 @@ class WindowProblem:
 
     def add_range(self, kf, lever, sat, rho, w):
         lib().go_problem_add_range(self.h, C.c_int(kf), _p(_f64(lever)), _p(_f64(sat)), C.c_double(rho), C.c_double(w))
+
+    def reset_state(self, poses, speed_bias=None):
+        pb = _f64(poses).reshape(-1, 7); sb = None if speed_bias is None else _f64(speed_bias).reshape(-1, 9)
+        lib().go_problem_set_state(self.h, _p(pb), _p(sb))
 
     def host_normal_eq(self):
         H = np.zeros((self.n, self.n)); g = np.zeros(self.n); c = np.zeros(1)
