@@ -441,6 +441,21 @@ def _set_allreduce(self, fn, user=None):
     self._chk(self._lib.glio_set_allreduce(self._h, fn, user))
 
 
+def _set_edges(self, slot, cp, pa, pb, s):
+    cp = np.ascontiguousarray(cp, np.float32).reshape(-1, 3); pa = np.ascontiguousarray(pa, np.float32).reshape(-1, 3)
+    pb = np.ascontiguousarray(pb, np.float32).reshape(-1, 3); s = np.ascontiguousarray(s, np.float64)
+    self._chk(self._lib.glio_set_edges(self._h, C.c_int(slot), _ptr(cp), _ptr(pa), _ptr(pb), _ptr(s), C.c_int64(len(s))))
+
+
+def _eval_edge(self, poses_body, want_jac=True):
+    pb = np.ascontiguousarray(poses_body, np.float64).reshape(-1, 7); W = len(pb)
+    H = np.zeros((W, 6, 6)) if want_jac else None; g = np.zeros((W, 6)) if want_jac else None; cost = np.zeros(W)
+    self._chk(self._lib.glio_eval_edge(self._h, C.c_int(W), _ptr(pb), _ptr(H), _ptr(g), _ptr(cost)))
+    return dict(H=H, g=g, cost=cost)
+
+
+Context.set_edges = _set_edges
+Context.eval_edge = _eval_edge
 Context.batch_declare_pairs = _batch_declare_pairs
 Context.batch_solve = _batch_solve
 Context.set_allreduce = _set_allreduce

@@ -22,6 +22,8 @@ struct Slot {
   int64_t n_match = 0;
   DevBuf<float4> s_cpw, s_nsd;   // selected subset
   int64_t n_sel = -1;            // -1: no selection -> all matches are active
+  DevBuf<float4> e_cps, e_pa, e_pb;  // edge correspondences (caller-provided)
+  int64_t n_edge = 0;
   // debug (keep_debug)
   DevBuf<uint8_t> dbg_status;
   DevBuf<int32_t> dbg_idx5;
@@ -30,7 +32,7 @@ struct Slot {
   DevBuf<double> dbg_plane;
   int64_t dbg_Q = 0;
   void release() {
-    scan.release(); m_cpw.release(); m_nsd.release(); m_src.release(); s_cpw.release(); s_nsd.release();
+    scan.release(); m_cpw.release(); m_nsd.release(); m_src.release(); s_cpw.release(); s_nsd.release(); e_cps.release(); e_pa.release(); e_pb.release();
     dbg_status.release(); dbg_idx5.release(); dbg_sqd5.release(); dbg_pm.release(); dbg_plane.release();
   }
 };
@@ -978,6 +980,66 @@ int glio_batch_solve(glio_ctx* c, int K, double* poses, double* speed_bias, glio
       if (sb) for (int i = 0; i < 9; ++i) speed_bias[9 * k + i] = x[(size_t)na * k + 7 + i];
     }
     fill_summary(S, n, summary, iter_log, iter_cap, step_log, step_cap);
+  });
+}
+
+
+// ---- K2e: edge correspondences are an input (the reference has no edge association)
+int glio_set_edges(glio_ctx* c, int slot, const float* cp, const float* pa, const float* pb, const double* s, int64_t n) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    Slot& sl = c->slot(slot);
+    sl.n_edge = 0;
+    if (n <= 0) return;
+    GLIO_REQUIRE(cp && pa && pb && s, GLIO_ERR_ARG, "null edge arrays");
+    std::vector<float4> h0(n), h1(n), h2(n);
+    for (int64_t i = 0; i < n; ++i) {
+      h0[i] = make_float4(cp[3 * i], cp[3 * i + 1], cp[3 * i + 2], (float)s[i]);
+      h1[i] = make_float4(pa[3 * i], pa[3 * i + 1], pa[3 * i + 2], 0.f);
+      h2[i] = make_float4(pb[3 * i], pb[3 * i + 1], pb[3 * i + 2], 0.f);
+    }
+    sl.e_cps.reserve(n); sl.e_pa.reserve(n); sl.e_pb.reserve(n);
+    GLIO_CUDA_TRY(cudaMemcpyAsync(sl.e_cps.p, h0.data(), n * sizeof(float4), cudaMemcpyHostToDevice, c->st));
+    GLIO_CUDA_TRY(cudaMemcpyAsync(sl.e_pa.p, h1.data(), n * sizeof(float4), cudaMemcpyHostToDevice, c->st));
+    GLIO_CUDA_TRY(cudaMemcpyAsync(sl.e_pb.p, h2.data(), n * sizeof(float4), cudaMemcpyHostToDevice, c->st));
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    sl.n_edge = n;
+  });
+}
+
+int glio_eval_edge(glio_ctx* c, int W, const double* poses_body, double* H, double* g, double* cost) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(W > 0 && W <= 4096 && poses_body, GLIO_ERR_ARG, "bad arguments");
+    std::vector<EdgeItem> items; std::vector<int> start(W + 1, 0);
+    for (int k = 0; k < W; ++k) {
+      start[k] = (int)items.size();
+      if ((size_t)k >= c->slots.size() || !c->slots[k]) continue;
+      Slot& sl = *c->slots[k];
+      for (int64_t o = 0; o < sl.n_edge; o += GLIO_ITEM_MAX) {
+        EdgeItem it; it.cps = sl.e_cps.p + o; it.pa = sl.e_pa.p + o; it.pb = sl.e_pb.p + o;
+        it.count = (int32_t)std::min<int64_t>(GLIO_ITEM_MAX, sl.n_edge - o); it.kf = k; items.push_back(it);
+      }
+    }
+    start[W] = (int)items.size();
+    DevBuf<EdgeItem> d_items; DevBuf<int> d_start; DevBuf<double> d_part, d_out, d_poses;
+    d_items.reserve(items.size() + 1); d_start.reserve(W + 1); d_part.reserve((items.size() + 1) * GLIO_NACC); d_out.reserve((size_t)W * GLIO_NACC); d_poses.reserve((size_t)W * 7);
+    if (!c->d_ticket.p) { c->d_ticket.reserve(1); GLIO_CUDA_TRY(cudaMemsetAsync(c->d_ticket.p, 0, sizeof(unsigned int), c->st)); }
+    if (!items.empty()) GLIO_CUDA_TRY(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(EdgeItem), cudaMemcpyHostToDevice, c->st));
+    GLIO_CUDA_TRY(cudaMemcpyAsync(d_start.p, start.data(), (W + 1) * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    GLIO_CUDA_TRY(cudaMemcpyAsync(d_poses.p, poses_body, (size_t)W * 7 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    const bool want_jac = H || g;
+    eval_edge_run(d_items.p, (int)items.size(), W, d_poses.p, eval_params(c), want_jac, d_part.p, d_out.p, d_start.p, c->d_ticket.p, c->st, c->lc);
+    std::vector<double> ho((size_t)W * GLIO_NACC);
+    GLIO_CUDA_TRY(cudaMemcpyAsync(ho.data(), d_out.p, ho.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    for (int k = 0; k < W; ++k) {
+      const double* o = ho.data() + (size_t)k * GLIO_NACC;
+      if (H) { int idx = 0; for (int p = 0; p < 6; ++p) for (int q = p; q < 6; ++q) { H[36 * k + 6 * p + q] = o[idx]; H[36 * k + 6 * q + p] = o[idx]; ++idx; } }
+      if (g) for (int p = 0; p < 6; ++p) g[6 * k + p] = o[21 + p];
+      if (cost) cost[k] = o[27];
+    }
+    d_items.release(); d_start.release(); d_part.release(); d_out.release(); d_poses.release();
   });
 }
 

@@ -198,6 +198,17 @@ void eval_unary_residuals_run(const float4* cpw, const float4* nsd, int64_t n, c
                               int jac_kind, double* d_r, double* d_J, cudaStream_t st, LaunchCounter& lc);
 
 
+// ---- K2e (eval.cu): edge factors
+struct EdgeItem {
+  const float4* cps;   // (cp.xyz, s)
+  const float4* pa;    // line point a
+  const float4* pb;    // line point b
+  int32_t count;
+  int32_t kf;
+};
+void eval_edge_run(const EdgeItem* d_items, int nitems, int W, const double* d_poses, const EvalParams& ep, bool want_jac,
+                   double* d_partials, double* d_out, const int* d_kf_item_start, unsigned int* d_ticket, cudaStream_t st, LaunchCounter& lc);
+
 // ---- K2b (eval.cu): binary plane factors
 struct BinItem {
   const float4* cpw;          // (cp.xyz, weight)

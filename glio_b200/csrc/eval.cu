@@ -238,6 +238,109 @@ void eval_unary_residuals_run(const float4* cpw, const float4* nsd, int64_t n, c
 }
 
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2e: point-to-edge residuals, LidarEdgeFactor (LidarKeyframeFactor.h:12-70; defined by the reference but never
+// instantiated):  lp = R(q) q_lb^-1 (cp - t_lb) + t ;  r = s |(lp-a) x (lp-b)| / |a-b|
+// closed form:  e = (lp-a) x (lp-b), gv = s/|a-b| ((a-b) x e/|e|), dr/dt = gv, dr/ddelta = 2 (R p_b x gv).
+// Inputs per residual: cp, a, b (float3 each) + s -> 3 x 16 B loads (s rides in cp.w).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool WANT_JAC>
+__global__ void __launch_bounds__(EV_T) k_eval_edge(const EdgeItem* __restrict__ items, int nitems, int W, const double* __restrict__ poses,
+                                                    EvalParams ep, double* __restrict__ partials, double* __restrict__ out,
+                                                    const int* __restrict__ kf_item_start, unsigned int* __restrict__ ticket) {
+  __shared__ KfFrame F;
+  __shared__ double red[EV_T / 32][NACC];
+  __shared__ bool is_last;
+  const EdgeItem it = items[blockIdx.x];
+  if (threadIdx.x == 0) {
+    const double* P = poses + 7 * it.kf;
+    double qn[4] = {P[3], P[4], P[5], P[6]};
+    double R[9]; quat_to_mat(qn, R);
+    const double n2 = ep.q_lb[0] * ep.q_lb[0] + ep.q_lb[1] * ep.q_lb[1] + ep.q_lb[2] * ep.q_lb[2] + ep.q_lb[3] * ep.q_lb[3];
+    double qi[4] = {ep.q_lb[0] / n2, -ep.q_lb[1] / n2, -ep.q_lb[2] / n2, -ep.q_lb[3] / n2};
+    quat_to_mat(qi, F.Rlbi);
+    mat_mul3(R, F.Rlbi, F.M);
+    F.t[0] = P[0]; F.t[1] = P[1]; F.t[2] = P[2];
+  }
+  __syncthreads();
+  double acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+  for (int i = threadIdx.x; i < it.count; i += EV_T) {
+    const float4 c4 = __ldg(&it.cps[i]);
+    const float4 a4 = __ldg(&it.pa[i]);
+    const float4 b4 = __ldg(&it.pb[i]);
+    const double s = (double)c4.w;
+    const double dx = (double)c4.x - ep.t_lb[0], dy = (double)c4.y - ep.t_lb[1], dz = (double)c4.z - ep.t_lb[2];
+    double a1[3]; mat_vec3(F.M, dx, dy, dz, a1);
+    const double lp[3] = {a1[0] + F.t[0], a1[1] + F.t[1], a1[2] + F.t[2]};
+    const double u[3] = {lp[0] - (double)a4.x, lp[1] - (double)a4.y, lp[2] - (double)a4.z};
+    const double v[3] = {lp[0] - (double)b4.x, lp[1] - (double)b4.y, lp[2] - (double)b4.z};
+    const double e[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+    const double de[3] = {(double)a4.x - (double)b4.x, (double)a4.y - (double)b4.y, (double)a4.z - (double)b4.z};
+    const double en = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+    const double dn = sqrt(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]);
+    double r = en / dn * s;
+    double scale;
+    acc[27] += huber_scale(r, ep.huber_delta, scale);
+    if (WANT_JAC) {
+      const double k = s / dn * scale / en;
+      const double gv[3] = {k * (de[1] * e[2] - de[2] * e[1]), k * (de[2] * e[0] - de[0] * e[2]), k * (de[0] * e[1] - de[1] * e[0])};
+      double J[6] = {gv[0], gv[1], gv[2], 2.0 * (a1[1] * gv[2] - a1[2] * gv[1]), 2.0 * (a1[2] * gv[0] - a1[0] * gv[2]), 2.0 * (a1[0] * gv[1] - a1[1] * gv[0])};
+      r *= scale;
+      int kk = 0;
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+#pragma unroll
+        for (int c = p; c < 6; ++c) acc[kk++] += J[p] * J[c];
+#pragma unroll
+      for (int p = 0; p < 6; ++p) acc[21 + p] += J[p] * r;
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = WANT_JAC ? 0 : 27; k < NACC; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NACC) {
+    double v = 0.0;
+    if (WANT_JAC || threadIdx.x == 27) {
+#pragma unroll
+      for (int w8 = 0; w8 < EV_T / 32; ++w8) v += red[w8][threadIdx.x];
+    }
+    partials[(size_t)blockIdx.x * NACC + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) { const unsigned int tk = atomicAdd(ticket, 1u); is_last = (tk == (unsigned)nitems - 1); }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int o = threadIdx.x; o < W * NACC; o += EV_T) {
+      const int kf = o / NACC, k = o - kf * NACC;
+      double v = 0.0;
+      for (int b = kf_item_start[kf]; b < kf_item_start[kf + 1]; ++b) v += partials[(size_t)b * NACC + k];
+      out[o] = v;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
+void eval_edge_run(const EdgeItem* d_items, int nitems, int W, const double* d_poses, const EvalParams& ep, bool want_jac,
+                   double* d_partials, double* d_out, const int* d_kf_item_start, unsigned int* d_ticket, cudaStream_t st, LaunchCounter& lc) {
+  if (nitems <= 0) { GLIO_CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)W * NACC * sizeof(double), st)); return; }
+  lc.begin(want_jac ? "k_eval_edge" : "k_eval_edge_cost", st);
+  if (want_jac) k_eval_edge<true><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, d_poses, ep, d_partials, d_out, d_kf_item_start, d_ticket);
+  else k_eval_edge<false><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, d_poses, ep, d_partials, d_out, d_kf_item_start, d_ticket);
+  lc.end(st);
+  GLIO_CUDA_TRY(cudaGetLastError());
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // K2b: binary (scan-to-multiscan) plane factors, BinaryLidarPlaneNormFactor (LidarKeyframeFactor.h:124-164):
 //   p_w = R(q_c) cp + t_c ;  N = R(q_o) n_l ;  c_w = R(q_o) c_l + t_o ;  r = s N.(p_w - c_w),  s = batch_score * weight

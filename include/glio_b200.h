@@ -232,6 +232,13 @@ int glio_batch_declare_pairs(glio_ctx* ctx, const int32_t* pairs_cur, const int3
  * (block (cur,oth): row = cur tangent, col = oth tangent, pairs in glio_batch_pair_list order), g[K*6], cost. */
 int glio_eval_binary(glio_ctx* ctx, int K, const double* poses, double* Hdiag, double* Hoff, double* g, double* cost);
 
+/* ---- K2e: point-to-edge residuals (LidarEdgeFactor, LidarKeyframeFactor.h:12-70).  The reference defines this factor
+ * but never instantiates it and has no edge association, so the correspondences are an input:
+ * cp[3n] scan point, pa/pb[3n] two points of the map line, s[n] weight.  Huber(huber_delta) as for the plane factors.
+ * glio_eval_edge returns the same per-keyframe 6x6 / 6 / cost blocks as glio_eval_unary (add them to the plane blocks). */
+int glio_set_edges(glio_ctx* ctx, int slot, const float* cp, const float* pa, const float* pb, const double* s, int64_t n);
+int glio_eval_edge(glio_ctx* ctx, int W, const double* poses_body, double* H, double* g, double* cost);
+
 /* ---- batch minimizer (replaces ceres::Solve of optimizeBatchWithLandMark, Estimator.cpp:3275-3284: SUBSPACE_DOGLEG,
  * nonmonotonic steps, max_num_iter iterations; options == NULL selects exactly those).  The normal equations are
  * block-banded (half bandwidth (max|cur-oth|+1)*nt - 1) and stored/factored in band form.  Host factors (IMU chain,

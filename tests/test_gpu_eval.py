@@ -92,3 +92,39 @@ def test_selection_index_list(setup, oracle):
             ctx.select(k, None)
     g2 = ctx.eval_unary(P["poses_init"])
     assert g2["cost"].sum() > g["cost"].sum()
+
+
+def test_edge_blocks(oracle):
+    """K2e: LidarEdgeFactor blocks vs the oracle's Jet autodiff of the functor (correspondences are an input)."""
+    from glio_b200 import api
+    rng = np.random.default_rng(9)
+    W, n = 3, 700
+    ctx = api.Context(0)
+    try:
+        P = synth.window_problem(W=W, Q=100, M=1000, seed=2)
+        poses = P["poses_init"]
+        kf, cp, pa, pb, s = [], [], [], [], []
+        for k in range(W):
+            a = rng.uniform(-20, 20, (n, 3)); d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+            b = a + d * rng.uniform(0.2, 1.0, (n, 1))
+            # scan point: near the line in the world, mapped into the lidar frame of keyframe k (noise -> some Huber outliers)
+            pw = a + d * rng.uniform(-1, 2, (n, 1)) + rng.normal(0, 0.08, (n, 3))
+            pbody = (pw - poses[k, :3]) @ synth.quat_to_R(poses[k, 3:])
+            pl = pbody @ synth.quat_to_R(P["q_lb"]).T + P["t_lb"]
+            ss = rng.uniform(1.0, 8.0, n)
+            ctx.set_edges(k, pl, a, b, ss)
+            kf.append(np.full(n, k, np.int32)); cp.append(pl.astype(np.float32)); pa.append(a.astype(np.float32)); pb.append(b.astype(np.float32))
+            s.append(ss.astype(np.float32).astype(np.float64))       # the weight rides in a float32 lane on the device
+        kf, cp, pa, pb, s = map(np.concatenate, (kf, cp, pa, pb, s))
+        o = oracle.eval_edge(poses, P["q_lb"], P["t_lb"], kf, cp, pa, pb, s, huber_delta=1.0, mode=0)
+        oc = oracle.eval_edge(poses, P["q_lb"], P["t_lb"], kf, cp, pa, pb, s, huber_delta=1.0, mode=1)
+        assert _rel(oc["H"], o["H"]) < 1e-10        # closed form == autodiff inside the oracle
+        g = ctx.eval_edge(poses)
+        for k in range(W):
+            assert _rel(g["H"][k], o["H"][6 * k:6 * k + 6, 6 * k:6 * k + 6]) < REL
+            assert _rel(g["g"][k], o["g"][6 * k:6 * k + 6]) < REL
+            ck = o["cost"][kf == k].sum()
+            assert abs(g["cost"][k] - ck) <= REL * ck
+        assert (o["cost"] > 0.5).any() and (o["cost"] < 0.5).any()
+    finally:
+        ctx.close()
