@@ -385,6 +385,35 @@ int glio_get_stats(glio_ctx* c, int64_t* knn_fallback_queries, int reset) {
   });
 }
 
+int glio_get_params(const glio_ctx* c, glio_params* out) {
+  if (!c || !out) return GLIO_ERR_ARG;
+  *out = c->prm;
+  return GLIO_OK;
+}
+
+// direct upload of a slot's match list (association done elsewhere, e.g. by the unmodified Estimator): the Ceres shim
+// uses this to move LidarPlaneNormFactor residual blocks onto the device.
+int glio_set_matches(glio_ctx* c, int slot, const float* cp, const float* nsd, const float* weight, int64_t n) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    Slot& sl = c->slot(slot);
+    sl.n_match = 0; sl.n_sel = -1; c->items_dirty = true;
+    if (n <= 0) return;
+    GLIO_REQUIRE(cp && nsd && weight, GLIO_ERR_ARG, "null match arrays");
+    std::vector<float4> h0(n), h1(n);
+    for (int64_t i = 0; i < n; ++i) {
+      h0[i] = make_float4(cp[3 * i], cp[3 * i + 1], cp[3 * i + 2], weight[i]);
+      h1[i] = make_float4(nsd[4 * i], nsd[4 * i + 1], nsd[4 * i + 2], nsd[4 * i + 3]);
+    }
+    sl.m_cpw.reserve(n); sl.m_nsd.reserve(n); sl.m_src.reserve(n);
+    GLIO_CUDA_TRY(cudaMemcpyAsync(sl.m_cpw.p, h0.data(), n * sizeof(float4), cudaMemcpyHostToDevice, c->st));
+    GLIO_CUDA_TRY(cudaMemcpyAsync(sl.m_nsd.p, h1.data(), n * sizeof(float4), cudaMemcpyHostToDevice, c->st));
+    GLIO_CUDA_TRY(cudaMemsetAsync(sl.m_src.p, 0, n * sizeof(int32_t), c->st));
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    sl.n_match = n;
+  });
+}
+
 int glio_get_match_counts(glio_ctx* c, int W, int64_t* n_match, int64_t* n_active) {
   if (!c) return GLIO_ERR_ARG;
   return guarded(c, [&] {
@@ -558,9 +587,9 @@ int glio_window_solve(glio_ctx* c, int W, double* poses, double* speed_bias, gli
     const int nt = sb ? 15 : 6, na = sb ? 16 : 7, n = W * nt;
     std::vector<ParamBlock> blocks;
     for (int k = 0; k < W; ++k) {
-      blocks.push_back(ParamBlock{na * k, 3, nt * k, 3, false});
-      blocks.push_back(ParamBlock{na * k + 3, 4, nt * k + 3, 3, true});
-      if (sb) blocks.push_back(ParamBlock{na * k + 7, 9, nt * k + 6, 9, false});
+      blocks.push_back(ParamBlock{na * k, 3, nt * k, 3, false, nullptr});
+      blocks.push_back(ParamBlock{na * k + 3, 4, nt * k + 3, 3, true, nullptr});
+      if (sb) blocks.push_back(ParamBlock{na * k + 7, 9, nt * k + 6, 9, false, nullptr});
     }
     SolverOptions so;
     so.max_num_iterations = o.max_num_iterations; so.dogleg_type = o.dogleg_type; so.use_nonmonotonic_steps = o.use_nonmonotonic_steps != 0;
@@ -925,9 +954,9 @@ int glio_batch_solve(glio_ctx* c, int K, double* poses, double* speed_bias, glio
     const int hb = (span + 1) * nt - 1;
     std::vector<ParamBlock> blocks;
     for (int k = 0; k < K; ++k) {
-      blocks.push_back(ParamBlock{na * k, 3, nt * k, 3, false});
-      blocks.push_back(ParamBlock{na * k + 3, 4, nt * k + 3, 3, true});
-      if (sb) blocks.push_back(ParamBlock{na * k + 7, 9, nt * k + 6, 9, false});
+      blocks.push_back(ParamBlock{na * k, 3, nt * k, 3, false, nullptr});
+      blocks.push_back(ParamBlock{na * k + 3, 4, nt * k + 3, 3, true, nullptr});
+      if (sb) blocks.push_back(ParamBlock{na * k + 7, 9, nt * k + 6, 9, false, nullptr});
     }
     SolverOptions so;
     so.max_num_iterations = o.max_num_iterations; so.dogleg_type = o.dogleg_type; so.use_nonmonotonic_steps = o.use_nonmonotonic_steps != 0;

@@ -25,6 +25,8 @@ struct ParamBlock {
   int amb_off, amb_size;   // offset/size in the ambient state vector
   int tan_off, tan_size;   // offset/size in the tangent vector
   bool quaternion;         // amb 4 (w,x,y,z) / tan 3, Ceres QuaternionParameterization
+  // optional custom LocalParameterization::Plus(x, delta, x_plus_delta) (Ceres shim); empty -> the two built-ins
+  std::function<void(const double*, const double*, double*)> plus_fn;
 };
 
 struct SolverOptions {
@@ -153,6 +155,7 @@ class TrustRegionDogleg {
 
   void plus(const double* x, const double* delta, double* out) const {
     for (auto& b : blocks_) {
+      if (b.plus_fn) { b.plus_fn(x + b.amb_off, delta + b.tan_off, out + b.amb_off); continue; }
       if (b.quaternion) detail::quat_plus(x + b.amb_off, delta + b.tan_off, out + b.amb_off);
       else for (int k = 0; k < b.amb_size; ++k) out[b.amb_off + k] = x[b.amb_off + k] + delta[b.tan_off + k];
     }

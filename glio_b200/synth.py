@@ -162,11 +162,14 @@ def window_problem(W=20, Q=100_000, M=1_000_000, seed=SEED0 + 2, n_boxes=30):
                 t_lb=T_LB.copy(), W=W, Q=Q, M=M, seed=seed)
 
 
-def batch_problem(K=200, Q=100_000, seed=SEED0 + 3, search_range=6, rng_range=50.0):
-    """cfg 3 / cfg 4 style batch problem: K keyframes, scans in the body frame."""
+def batch_problem(K=200, Q=100_000, seed=SEED0 + 3, search_range=6, rng_range=50.0, frames=None):
+    """cfg 3 / cfg 4 style batch problem: K keyframes, scans in the body frame.  Every scan has its own RNG stream
+    (seed, k), so a rank of a sharded run can generate only the frames it holds (`frames`) and still agree with the
+    others; scans[k] is None for frames not requested."""
     rng = np.random.default_rng(seed)
     scene = Scene(-60.0, K + 60.0, rng)
     truth = trajectory(K, rng)
     init = perturb(truth, rng, sig_t=0.03, sig_r_deg=0.2)
-    scans = [scan_in_body_frame(scene, truth[k], Q, rng, rng_range) for k in range(K)]
+    want = set(range(K)) if frames is None else set(int(f) for f in frames)
+    scans = [scan_in_body_frame(scene, truth[k], Q, np.random.default_rng([seed, k]), rng_range) if k in want else None for k in range(K)]
     return dict(scans=scans, poses_true=truth, poses_init=init, K=K, Q=Q, search_range=search_range, seed=seed)

@@ -104,6 +104,11 @@ int glio_assoc_scan_to_map(glio_ctx* ctx, int slot, const float* scan_xyz, int64
 int glio_window_set_scans(glio_ctx* ctx, int W, const float* const* scans, const int64_t* Q, int stride_floats, int mem);
 int glio_window_associate(glio_ctx* ctx, int W, const double* poses_body, int64_t* n_match /*W*/);
 
+/* direct upload of a slot's match list when the association was done elsewhere (e.g. by an unmodified Estimator through
+ * PCL): cp[3n], nsd[4n] = (weight*n, weight*d), weight[n]; score = lidar_const*weight.  Used by the Ceres shim. */
+int glio_set_matches(glio_ctx* ctx, int slot, const float* cp, const float* nsd, const float* weight, int64_t n);
+int glio_get_params(const glio_ctx* ctx, glio_params* out);
+
 /* copy-out of one slot's matches (parity tests, and the Ceres shim's host view).  Any pointer may be NULL.
  *   cp[3n] float (scan-frame point), nsd[4n] float (weight*n, weight*d), weight[n] float, src[n] int32
  *   (index of the match's scan point).  score = lidar_const * (double)weight. */
