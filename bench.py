@@ -172,7 +172,7 @@ def run_glio(args, rank, world, local_rank):
         ctx.set_map(m)
         ctx.window_set_scans(scans)
         ctx.window_associate(P["poses_init"])
-        r = ctx.window_solve(P["poses_init"], sb0, hf, opts)
+        r = ctx.window_solve(P["poses_init"], sb0, hf, opts, band=29)
         return len(r["steps"]), r
 
     def timed_run(m, scans, nsteps):
@@ -211,6 +211,17 @@ def run_glio(args, rank, world, local_rank):
     for _ in range(2):
         one_step(hmap, hscans)
     iters_e, ms_e, wall_e = timed_run(hmap, hscans, args.steps)
+    # wall-clock split of one resident step (every call ends synchronised, so these add up to the step)
+    split = {}
+    for _ in range(3):
+        torch.cuda.synchronize(); tf = time.perf_counter()
+        with torch.cuda.stream(st):
+            flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); ctx.set_map(dmap); t1 = time.perf_counter(); ctx.window_set_scans(dscans); t2 = time.perf_counter()
+        ctx.window_associate(P["poses_init"]); t3 = time.perf_counter(); ctx.window_solve(P["poses_init"], sb0, hf, opts, band=29); t4 = time.perf_counter()
+        split = dict(l2_flush_ms=round(1e3 * (t0 - tf), 3), set_map_ms=round(1e3 * (t1 - t0), 3), set_scans_ms=round(1e3 * (t2 - t1), 3),
+                     associate_ms=round(1e3 * (t3 - t2), 3), solve_ms=round(1e3 * (t4 - t3), 3))
     _, rlast = one_step(dmap, dscans)
 
     tmax, tmax_e, it_sum, it_sum_e = ms, ms_e, iters, iters_e
@@ -268,7 +279,7 @@ def run_glio(args, rank, world, local_rank):
                             parallelism="replicas only (window path does not shard)" if world > 1 else "1 GPU",
                             l2="256 MB flush between steps inside the timed region; per-step working set ~300 MB > 126 MB L2; "
                                "K2 re-reads the 64 MB residual table every iteration as the real solve does",
-                            host_wall_ms_per_step=1e3 * wall / args.steps, knn_fallback_queries_per_step=n_fallback / args.steps, kernels=kern),
+                            host_wall_ms_per_step=1e3 * wall / args.steps, knn_extra_rings_per_step=n_fallback / args.steps, wall_split=split, kernels=kern),
                 e2e=dict(value=e2e, unit="iterations/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=tmax_e / args.steps),
                 gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
     print(json.dumps(line))

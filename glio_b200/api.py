@@ -317,7 +317,7 @@ class HostFactorSet:
             pass
 
 
-def _window_solve(self, poses, speed_bias=None, host_factors=None, options=None, max_log=256):
+def _window_solve(self, poses, speed_bias=None, host_factors=None, options=None, max_log=64, band=None):
     """ceres::Solve for the window problem (Estimator.cpp:2424-2433).  Returns dict(poses, speed_bias, summary, iterations, steps)."""
     pb = np.array(poses, np.float64).reshape(-1, 7).copy(); W = len(pb)
     sb = None if speed_bias is None else np.array(speed_bias, np.float64).reshape(W, 9).copy()
@@ -330,8 +330,14 @@ def _window_solve(self, poses, speed_bias=None, host_factors=None, options=None,
         fn, user = host_factors.callback
     else:
         fn, user = host_factors, None          # a HOST_FACTORS_FN instance
-    self._chk(self._lib.glio_window_solve(self._h, C.c_int(W), _ptr(pb), _ptr(sb), fn, user, C.byref(opt), C.byref(summ), log,
-                                          C.c_int(max_log), _ptr(steps), C.c_int64(steps.size)))
+    if band is not None and isinstance(host_factors, HostFactorSet):
+        # host factors straight into band storage (band = half bandwidth, e.g. 29 for prior + chain with speed-bias)
+        bfn = C.cast(self._lib.glio_hf_evaluate_band, HOST_FACTORS_BAND_FN)
+        self._chk(self._lib.glio_window_solve_band(self._h, C.c_int(W), _ptr(pb), _ptr(sb), bfn, C.c_int(band), host_factors._h, C.byref(opt),
+                                                   C.byref(summ), log, C.c_int(max_log), _ptr(steps), C.c_int64(steps.size)))
+    else:
+        self._chk(self._lib.glio_window_solve(self._h, C.c_int(W), _ptr(pb), _ptr(sb), fn, user, C.byref(opt), C.byref(summ), log,
+                                              C.c_int(max_log), _ptr(steps), C.c_int64(steps.size)))
     return dict(poses=pb, speed_bias=sb, summary=summ, iterations=iterations_to_dicts(log, min(summ.num_iterations, max_log)),
                 steps=steps[:summ.num_valid_steps])
 

@@ -55,20 +55,25 @@ __global__ void __launch_bounds__(256) k_order_scatter(GridDesc grid, int64_t Qt
 }
 
 // ---- top-5 by (distance, index) -------------------------------------------------------------------
+// One 64-bit key per neighbour: (bits of the non-negative float distance) << 32 | index.  Unsigned key order ==
+// lexicographic (distance, index) order, so ties are broken by index exactly like a stable sort by (distance, index).
 struct Top5 {
-  float d0, d1, d2, d3, d4;
-  int i0, i1, i2, i3, i4;
+  unsigned long long k0, k1, k2, k3, k4;
 };
-__device__ __forceinline__ bool lex_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
-#define GLIO_CSWAP(DA, IA, DB, IB) \
-  if (lex_less(DB, IB, DA, IA)) { float _d = DA; DA = DB; DB = _d; int _i = IA; IA = IB; IB = _i; }
+__device__ __forceinline__ unsigned long long make_key(float d, int id) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)id; }
+__device__ __forceinline__ float key_dist(unsigned long long k) { return __uint_as_float((unsigned int)(k >> 32)); }
+__device__ __forceinline__ int key_idx(unsigned long long k) { return (int)(unsigned int)(k & 0xffffffffull); }
+constexpr unsigned long long KEY_EMPTY = 0x7f8000007fffffffull;   // (+inf, INT_MAX)
+__device__ __forceinline__ void top5_init(Top5& t) { t.k0 = t.k1 = t.k2 = t.k3 = t.k4 = KEY_EMPTY; }
+#define GLIO_KSWAP(A, B) { const unsigned long long _lo = (A) < (B) ? (A) : (B); const unsigned long long _hi = (A) < (B) ? (B) : (A); (A) = _lo; (B) = _hi; }
 __device__ __forceinline__ void top5_push(Top5& t, float d, int id) {
-  if (lex_less(d, id, t.d4, t.i4)) {
-    t.d4 = d; t.i4 = id;
-    GLIO_CSWAP(t.d3, t.i3, t.d4, t.i4)
-    GLIO_CSWAP(t.d2, t.i2, t.d3, t.i3)
-    GLIO_CSWAP(t.d1, t.i1, t.d2, t.i2)
-    GLIO_CSWAP(t.d0, t.i0, t.d1, t.i1)
+  const unsigned long long k = make_key(d, id);
+  if (k < t.k4) {
+    t.k4 = k;
+    GLIO_KSWAP(t.k3, t.k4)
+    GLIO_KSWAP(t.k2, t.k3)
+    GLIO_KSWAP(t.k1, t.k2)
+    GLIO_KSWAP(t.k0, t.k1)
   }
 }
 
@@ -82,6 +87,18 @@ __device__ __forceinline__ void top5_push(Top5& t, float d, int id) {
 // box covers the gate radius (anything unseen then fails the radius gate anyway).
 // Intermediate results are written in sorted order, structure-of-arrays: coalesced here and in K1b.
 // ---------------------------------------------------------------------------------------------------
+// ---- packed fp32x2 arithmetic (Blackwell FADD2/FMUL2/FFMA2) for the candidate PRE-FILTER only.
+// ptxas contracts packed mul+add into FFMA2 even for .rn operands and under -fmad=false, so packed results may
+// differ from the reference's unfused ((dx*dx)+dy*dy)+dz*dz by a few ulps.  They are therefore used only to reject
+// candidates that are clearly farther than the current 5th distance (with a 1e-6 relative margin); every candidate
+// that might matter is re-evaluated with the exact scalar l2_simple() before it can enter the top-5.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float a, float b) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 constexpr int KNN_WARPS = 4;
 constexpr int KNN_SPAN_MAX = 12;
 
@@ -97,7 +114,8 @@ struct SearchArgs {
 };
 
 __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
-  __shared__ float4 stage[KNN_WARPS][32];
+  __shared__ __align__(16) float sx[KNN_WARPS][32], sy[KNN_WARPS][32], sz[KNN_WARPS][32];
+  __shared__ __align__(16) int si[KNN_WARPS][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t p = ((int64_t)blockIdx.x * KNN_WARPS + wid) * 32 + lane;
   const bool active = p < a.Qt;
@@ -107,8 +125,8 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
   if (active) { const float4 q4 = a.pm[a.order[p]]; qx = q4.x; qy = q4.y; qz = q4.z; }
   const int cx = cell_coord(qx, G.ox, G.inv_cell), cy = cell_coord(qy, G.oy, G.inv_cell), cz = cell_coord(qz, G.oz, G.inv_cell);
   Top5 t;
-  t.d0 = t.d1 = t.d2 = t.d3 = t.d4 = INF;
-  t.i0 = t.i1 = t.i2 = t.i3 = t.i4 = 0x7fffffff;
+  top5_init(t);
+  const f32x2_t qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
   const int rmax = (int)ceilf((sqrtf(a.gate_sq) + 2e-3f) * G.inv_cell) + 1;
   // far outside the grid: nothing within the gate radius
   const bool far_out = cx < -rmax || cy < -rmax || cz < -rmax || cx >= G.nx + rmax || cy >= G.ny + rmax || cz >= G.nz + rmax;
@@ -128,9 +146,19 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
       const int x0 = max(xa, 0), x1 = min(xb, G.nx - 1);
       const int z0 = max(lcz - r, 0), z1 = min(lcz + r, G.nz - 1);
       const int y0 = max(lcy - r, 0), y1 = min(lcy + r, G.ny - 1);
-      for (int z = z0; z <= z1; ++z) {
-        const bool zshell = (z == lcz - r) || (z == lcz + r);
-        for (int y = y0; y <= y1; ++y) {
+      const int nzr = z1 - z0 + 1, nyr = y1 - y0 + 1;
+      for (int ri = 0; ri < nzr * nyr; ++ri) {
+        {
+          // visit order: for the first ring the query's own row first, then the rest (the 5th distance shrinks early
+          // and the pre-filter rejects more); later rings in plain row order
+          int zz = z0 + ri / nyr, yy = y0 + ri % nyr;
+          if (r == 1 && lcz >= z0 && lcz <= z1 && lcy >= y0 && lcy <= y1) {
+            const int own = (lcz - z0) * nyr + (lcy - y0);
+            const int rj = ri == 0 ? own : (ri <= own ? ri - 1 : ri);
+            zz = z0 + rj / nyr; yy = y0 + rj % nyr;
+          }
+          const int z = zz, y = yy;
+          const bool zshell = (z == lcz - r) || (z == lcz + r);
           const int row = (z * G.ny + y) * G.nx;
           const bool shell = r == 1 || zshell || (y == lcy - r) || (y == lcy + r);
           // shell rows are new: whole x-range; inner rows were scanned up to [xa+1, xb-1]: only the two end cells
@@ -144,13 +172,22 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
             }
             for (int base = s; base < e; base += 32) {
               const int k = base + lane;
-              if (k < e) stage[wid][lane] = __ldg(&G.pts[k]);
+              float4 pt = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);       // filler for the odd lane of the last pair (never pushed)
+              if (k < e) pt = __ldg(&G.pts[k]);
+              sx[wid][lane] = pt.x; sy[wid][lane] = pt.y; sz[wid][lane] = pt.z; si[wid][lane] = __float_as_int(pt.w);
               __syncwarp();
               const int cnt = min(32, e - base);
               if (unproven) {
-                for (int j = 0; j < cnt; ++j) {
-                  const float4 c = stage[wid][j];
-                  top5_push(t, l2_simple(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+                const f32x2_t* px2 = reinterpret_cast<const f32x2_t*>(sx[wid]);
+                const f32x2_t* py2 = reinterpret_cast<const f32x2_t*>(sy[wid]);
+                const f32x2_t* pz2 = reinterpret_cast<const f32x2_t*>(sz[wid]);
+                for (int j = 0; j < cnt; j += 2) {
+                  const f32x2_t dx = sub2(qx2, px2[j >> 1]), dy = sub2(qy2, py2[j >> 1]), dz = sub2(qz2, pz2[j >> 1]);
+                  const f32x2_t a2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                  float a0, a1; unpack2(a2, a0, a1);
+                  const float thr = key_dist(t.k4) * 1.000001f;             // +inf until five candidates were seen
+                  if (a0 <= thr) top5_push(t, l2_simple(qx, qy, qz, sx[wid][j], sy[wid][j], sz[wid][j]), si[wid][j]);
+                  if (j + 1 < cnt && a1 <= key_dist(t.k4) * 1.000001f) top5_push(t, l2_simple(qx, qy, qz, sx[wid][j + 1], sy[wid][j + 1], sz[wid][j + 1]), si[wid][j + 1]);
                 }
               }
               __syncwarp();
@@ -168,7 +205,7 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
         if (lcz - r > 0)          b = fminf(b, qz - (G.oz + (float)(lcz - r) * G.cell));
         if (lcz + r < G.nz - 1)   b = fminf(b, (G.oz + (float)(lcz + r + 1) * G.cell) - qz);
         const float bs = b * 0.999f - 2e-3f;   // safety: float rounding of cell assignment / face positions
-        if ((b == INF) || (bs > 0.f && t.d4 <= bs * bs)) unproven = false;
+        if ((b == INF) || (bs > 0.f && key_dist(t.k4) <= bs * bs)) unproven = false;
         else ++extra_rings;
       }
       if (!__ballot_sync(0xffffffffu, unproven)) break;
@@ -180,10 +217,10 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
     if (lane == 0 && extra_rings) atomicAdd(a.n_fallback, extra_rings);
   }
   if (active) {
-    a.knn_idx[0 * a.Qt + p] = t.i0; a.knn_idx[1 * a.Qt + p] = t.i1; a.knn_idx[2 * a.Qt + p] = t.i2;
-    a.knn_idx[3 * a.Qt + p] = t.i3; a.knn_idx[4 * a.Qt + p] = t.i4;
-    a.knn_sqd[0 * a.Qt + p] = t.d0; a.knn_sqd[1 * a.Qt + p] = t.d1; a.knn_sqd[2 * a.Qt + p] = t.d2;
-    a.knn_sqd[3 * a.Qt + p] = t.d3; a.knn_sqd[4 * a.Qt + p] = t.d4;
+    a.knn_idx[0 * a.Qt + p] = key_idx(t.k0); a.knn_idx[1 * a.Qt + p] = key_idx(t.k1); a.knn_idx[2 * a.Qt + p] = key_idx(t.k2);
+    a.knn_idx[3 * a.Qt + p] = key_idx(t.k3); a.knn_idx[4 * a.Qt + p] = key_idx(t.k4);
+    a.knn_sqd[0 * a.Qt + p] = key_dist(t.k0); a.knn_sqd[1 * a.Qt + p] = key_dist(t.k1); a.knn_sqd[2 * a.Qt + p] = key_dist(t.k2);
+    a.knn_sqd[3 * a.Qt + p] = key_dist(t.k3); a.knn_sqd[4 * a.Qt + p] = key_dist(t.k4);
   }
 }
 

@@ -46,6 +46,7 @@ struct glio_ctx {
   std::string err;
   LaunchCounter lc;
 
+  int eval_slots = 296;        // resident evaluation blocks: 2 per SM (set from the device at creation)
   float pts_per_cell = 16.0f;   // target points per occupied grid cell (tuning hook: env GLIO_PTS_PER_CELL)
   GridBuild map;
   bool has_map = false;
@@ -216,6 +217,12 @@ void build_items(glio_ctx* c, int W) {
   if (!c->items_dirty && c->items_W == W) return;
   std::vector<EvalItem> items;
   std::vector<int> start(W + 1, 0);
+  // item size: the whole launch should be about one wave of 2 resident blocks per SM (less per-item reduction
+  // overhead, no wave-quantisation tail), but never below GLIO_ITEM_MAX residuals per item
+  int64_t n_total = 0;
+  for (int k = 0; k < W && (size_t)k < c->slots.size(); ++k) if (c->slots[k]) n_total += c->slots[k]->n_sel >= 0 ? c->slots[k]->n_sel : c->slots[k]->n_match;
+  int64_t item_size = (n_total + c->eval_slots - 1) / std::max(c->eval_slots, 1);
+  item_size = std::max<int64_t>(GLIO_ITEM_MAX, ((item_size + 255) / 256) * 256);
   for (int k = 0; k < W; ++k) {
     start[k] = (int)items.size();
     if ((size_t)k >= c->slots.size() || !c->slots[k]) continue;
@@ -224,8 +231,10 @@ void build_items(glio_ctx* c, int W) {
     const int64_t n = sel ? sl.n_sel : sl.n_match;
     const float4* cpw = sel ? sl.s_cpw.p : sl.m_cpw.p;
     const float4* nsd = sel ? sl.s_nsd.p : sl.m_nsd.p;
-    for (int64_t o = 0; o < n; o += GLIO_ITEM_MAX) {
-      EvalItem it; it.cpw = cpw + o; it.nsd = nsd + o; it.count = (int32_t)std::min<int64_t>(GLIO_ITEM_MAX, n - o); it.kf = k;
+    const int64_t parts = std::max<int64_t>(1, (n + item_size - 1) / item_size);
+    const int64_t per = ((n + parts - 1) / parts + 255) / 256 * 256;      // equal, 256-aligned parts
+    for (int64_t o = 0; o < n; o += per) {
+      EvalItem it; it.cpw = cpw + o; it.nsd = nsd + o; it.count = (int32_t)std::min<int64_t>(per, n - o); it.kf = k;
       items.push_back(it);
     }
   }
@@ -312,6 +321,7 @@ int glio_create(int device, const glio_params* params, glio_ctx** out) {
     if (params) c->prm = *params; else glio_default_params(&c->prm);
     if (const char* e = getenv("GLIO_PTS_PER_CELL")) { const float v = (float)atof(e); if (v > 0.1f && v < 1000.f) c->pts_per_cell = v; }
     GLIO_CUDA_TRY(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    { int sms = 148; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->eval_slots = 2 * sms; }
   });
   if (rc != GLIO_OK) { delete c; return rc; }
   *out = c;
@@ -576,9 +586,10 @@ void glio_default_solver_options(glio_solver_options* o) {
   o->fuse_candidate_jacobian = 1;
 }
 
-int glio_window_solve(glio_ctx* c, int W, double* poses, double* speed_bias, glio_host_factors_fn host_factors, void* user,
-                      const glio_solver_options* options, glio_solver_summary* summary, glio_iteration* iter_log, int iter_cap,
-                      double* step_log, int64_t step_cap) {
+static int window_solve_impl(glio_ctx* c, int W, double* poses, double* speed_bias, glio_host_factors_fn host_factors,
+                             glio_host_factors_band_fn host_band, int hb_hint, void* user,
+                             const glio_solver_options* options, glio_solver_summary* summary, glio_iteration* iter_log, int iter_cap,
+                             double* step_log, int64_t step_cap) {
   if (!c) return GLIO_ERR_ARG;
   return guarded(c, [&] {
     GLIO_REQUIRE(W > 0 && W <= 4096 && poses, GLIO_ERR_ARG, "bad arguments");
@@ -620,6 +631,18 @@ int glio_window_solve(glio_ctx* c, int W, double* poses, double* speed_bias, gli
         std::fill(g, g + n, 0.0);
         for (int k = 0; k < W; ++k) for (int p = 0; p < 6; ++p) g[nt * k + p] = c->h_out.p[(size_t)k * GLIO_NACC + 21 + p];
       }
+      if (host_band) {
+        // host factors accumulate straight into the band matrix (no dense n x n scratch)
+        if (want_jac) H->reset(n, hb_hint >= 5 ? hb_hint : n - 1);
+        if (host_band(user, W, pz.data(), sb ? sz.data() : nullptr, want_jac ? 1 : 0, want_jac ? H->a.data() : nullptr, want_jac ? H->hb : 0, g, &ct) != 0) return false;
+        if (want_jac) for (int k = 0; k < W; ++k) {
+          const double* ob = c->h_out.p + (size_t)k * GLIO_NACC;
+          int idx = 0;
+          for (int p = 0; p < 6; ++p) for (int q = p; q < 6; ++q) { H->at(nt * k + q, nt * k + p) += ob[idx]; ++idx; }
+        }
+        *cost = ct;
+        return std::isfinite(ct);
+      }
       if (host_factors) {
         if (want_jac) Hd.assign((size_t)n * n, 0.0);
         if (host_factors(user, W, pz.data(), sb ? sz.data() : nullptr, want_jac ? 1 : 0, want_jac ? Hd.data() : nullptr, g, &ct) != 0) return false;
@@ -652,6 +675,18 @@ int glio_window_solve(glio_ctx* c, int W, double* poses, double* speed_bias, gli
     }
     fill_summary(S, n, summary, iter_log, iter_cap, step_log, step_cap);
   });
+}
+
+int glio_window_solve(glio_ctx* c, int W, double* poses, double* speed_bias, glio_host_factors_fn host_factors, void* user,
+                      const glio_solver_options* options, glio_solver_summary* summary, glio_iteration* iter_log, int iter_cap,
+                      double* step_log, int64_t step_cap) {
+  return window_solve_impl(c, W, poses, speed_bias, host_factors, nullptr, -1, user, options, summary, iter_log, iter_cap, step_log, step_cap);
+}
+
+int glio_window_solve_band(glio_ctx* c, int W, double* poses, double* speed_bias, glio_host_factors_band_fn host_factors, int half_bandwidth,
+                           void* user, const glio_solver_options* options, glio_solver_summary* summary, glio_iteration* iter_log,
+                           int iter_cap, double* step_log, int64_t step_cap) {
+  return window_solve_impl(c, W, poses, speed_bias, nullptr, host_factors, half_bandwidth, user, options, summary, iter_log, iter_cap, step_log, step_cap);
 }
 
 int glio_eval_unary_residuals(glio_ctx* c, int slot, const double pose_body[7], int jac_kind, int64_t capacity, double* r, double* J, int64_t* n_out) {

@@ -59,11 +59,57 @@ struct KfFrame {           // per keyframe, prepared in shared memory
   double q[4];
 };
 
+// per-residual math of the unary plane factor; M, t (and R_lb^-1, q for the marginalisation variant) live in registers
 template <bool WANT_JAC, int JAC_KIND>
-__global__ void __launch_bounds__(EV_T) k_eval_unary(const EvalItem* __restrict__ items, int nitems, int W,
-                                                     const double* __restrict__ poses, EvalParams ep,
-                                                     double* __restrict__ partials, double* __restrict__ out,
-                                                     const int* __restrict__ kf_item_start, unsigned int* __restrict__ ticket) {
+__device__ __forceinline__ void unary_accumulate(const float4 c4, const float4 n4, const double (&M)[9], const double (&t)[3],
+                                                 const KfFrame& F, const EvalParams& ep, double (&acc)[NACC]) {
+  const double s = ep.lidar_const * (double)c4.w;            // Estimator.cpp:3692 score = lidar_const*weight
+  const double dx = (double)c4.x - ep.t_lb[0], dy = (double)c4.y - ep.t_lb[1], dz = (double)c4.z - ep.t_lb[2];
+  double a[3]; mat_vec3(M, dx, dy, dz, a);                   // a = R(q) q_lb^-1 (cp - t_lb)
+  const double nx = (double)n4.x, ny = (double)n4.y, nz = (double)n4.z;
+  double r = s * (nx * (a[0] + t[0]) + ny * (a[1] + t[1]) + nz * (a[2] + t[2]) + (double)n4.w);
+  double scale;
+  acc[27] += huber_scale(r, ep.huber_delta, scale);
+  if (WANT_JAC) {
+    double J[6];
+    const double ss = s * scale;
+    J[0] = ss * nx; J[1] = ss * ny; J[2] = ss * nz;
+    if (JAC_KIND == 0) {
+      // tangent (Ceres QuaternionParameterization):  2 s (a x n)
+      const double s2 = 2.0 * ss;
+      J[3] = s2 * (a[1] * nz - a[2] * ny);
+      J[4] = s2 * (a[2] * nx - a[0] * nz);
+      J[5] = s2 * (a[0] * ny - a[1] * nx);
+    } else {
+      // ambient x,y,z columns (MarginalizationFactor.cpp:9-12):
+      //   s [ 2w (p_b x n) + 2( (u.p_b) n + (n.u) p_b - 2 (n.p_b) u ) ]
+      double pb[3]; mat_vec3(F.Rlbi, dx, dy, dz, pb);
+      const double w = F.q[0], ux = F.q[1], uy = F.q[2], uz = F.q[3];
+      const double udp = ux * pb[0] + uy * pb[1] + uz * pb[2];
+      const double ndu = nx * ux + ny * uy + nz * uz;
+      const double ndp = nx * pb[0] + ny * pb[1] + nz * pb[2];
+      J[3] = ss * (2.0 * w * (pb[1] * nz - pb[2] * ny) + 2.0 * (udp * nx + ndu * pb[0] - 2.0 * ndp * ux));
+      J[4] = ss * (2.0 * w * (pb[2] * nx - pb[0] * nz) + 2.0 * (udp * ny + ndu * pb[1] - 2.0 * ndp * uy));
+      J[5] = ss * (2.0 * w * (pb[0] * ny - pb[1] * nx) + 2.0 * (udp * nz + ndu * pb[2] - 2.0 * ndp * uz));
+    }
+    r *= scale;
+    int k = 0;
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+#pragma unroll
+      for (int c = p; c < 6; ++c) acc[k++] += J[p] * J[c];
+#pragma unroll
+    for (int p = 0; p < 6; ++p) acc[21 + p] += J[p] * r;
+  }
+}
+
+// One block per work item (a run of one keyframe's residuals, sized so the whole launch is about one wave of
+// 2 blocks/SM).  Loads are issued two iterations ahead of their use (4 x 16 B in flight per thread).
+template <bool WANT_JAC, int JAC_KIND>
+__global__ void __launch_bounds__(EV_T, 2) k_eval_unary(const EvalItem* __restrict__ items, int nitems, int W,
+                                                        const double* __restrict__ poses, EvalParams ep,
+                                                        double* __restrict__ partials, double* __restrict__ out,
+                                                        const int* __restrict__ kf_item_start, unsigned int* __restrict__ ticket) {
   __shared__ KfFrame F;
   __shared__ double red[EV_T / 32][NACC];
   __shared__ bool is_last;
@@ -81,51 +127,29 @@ __global__ void __launch_bounds__(EV_T) k_eval_unary(const EvalItem* __restrict_
     F.q[0] = qn[0]; F.q[1] = qn[1]; F.q[2] = qn[2]; F.q[3] = qn[3];
   }
   __syncthreads();
+  double M[9], t[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) M[k] = F.M[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) t[k] = F.t[k];
 
   double acc[NACC];
 #pragma unroll
   for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
 
-  for (int i = threadIdx.x; i < it.count; i += EV_T) {
-    const float4 c4 = __ldg(&it.cpw[i]);
-    const float4 n4 = __ldg(&it.nsd[i]);
-    const double s = ep.lidar_const * (double)c4.w;            // Estimator.cpp:3692 score = lidar_const*weight
-    const double dx = (double)c4.x - ep.t_lb[0], dy = (double)c4.y - ep.t_lb[1], dz = (double)c4.z - ep.t_lb[2];
-    double a[3]; mat_vec3(F.M, dx, dy, dz, a);                 // a = R(q) q_lb^-1 (cp - t_lb)
-    const double nx = (double)n4.x, ny = (double)n4.y, nz = (double)n4.z;
-    double r = s * (nx * (a[0] + F.t[0]) + ny * (a[1] + F.t[1]) + nz * (a[2] + F.t[2]) + (double)n4.w);
-    double scale;
-    acc[27] += huber_scale(r, ep.huber_delta, scale);
-    if (WANT_JAC) {
-      double J[6];
-      const double ss = s * scale;
-      J[0] = ss * nx; J[1] = ss * ny; J[2] = ss * nz;
-      if (JAC_KIND == 0) {
-        // tangent (Ceres QuaternionParameterization):  2 s (a x n)
-        J[3] = 2.0 * ss * (a[1] * nz - a[2] * ny);
-        J[4] = 2.0 * ss * (a[2] * nx - a[0] * nz);
-        J[5] = 2.0 * ss * (a[0] * ny - a[1] * nx);
-      } else {
-        // ambient x,y,z columns (MarginalizationFactor.cpp:9-12):
-        //   s [ 2w (p_b x n) + 2( (u.p_b) n + (n.u) p_b - 2 (n.p_b) u ) ]
-        double pb[3]; mat_vec3(F.Rlbi, dx, dy, dz, pb);
-        const double w = F.q[0], ux = F.q[1], uy = F.q[2], uz = F.q[3];
-        const double udp = ux * pb[0] + uy * pb[1] + uz * pb[2];
-        const double ndu = nx * ux + ny * uy + nz * uz;
-        const double ndp = nx * pb[0] + ny * pb[1] + nz * pb[2];
-        J[3] = ss * (2.0 * w * (pb[1] * nz - pb[2] * ny) + 2.0 * (udp * nx + ndu * pb[0] - 2.0 * ndp * ux));
-        J[4] = ss * (2.0 * w * (pb[2] * nx - pb[0] * nz) + 2.0 * (udp * ny + ndu * pb[1] - 2.0 * ndp * uy));
-        J[5] = ss * (2.0 * w * (pb[0] * ny - pb[1] * nx) + 2.0 * (udp * nz + ndu * pb[2] - 2.0 * ndp * uz));
-      }
-      r *= scale;
-      int k = 0;
-#pragma unroll
-      for (int p = 0; p < 6; ++p)
-#pragma unroll
-        for (int c = p; c < 6; ++c) acc[k++] += J[p] * J[c];
-#pragma unroll
-      for (int p = 0; p < 6; ++p) acc[21 + p] += J[p] * r;
-    }
+  const int n = it.count;
+  int i = threadIdx.x;
+  // software pipeline, depth 2
+  float4 c0, n0, c1, n1;
+  if (i < n) { c0 = __ldg(&it.cpw[i]); n0 = __ldg(&it.nsd[i]); }
+  if (i + EV_T < n) { c1 = __ldg(&it.cpw[i + EV_T]); n1 = __ldg(&it.nsd[i + EV_T]); }
+  for (; i < n; i += 2 * EV_T) {
+    const float4 ca = c0, na = n0, cb = c1, nb = n1;
+    const bool has_b = i + EV_T < n;
+    if (i + 2 * EV_T < n) { c0 = __ldg(&it.cpw[i + 2 * EV_T]); n0 = __ldg(&it.nsd[i + 2 * EV_T]); }
+    if (i + 3 * EV_T < n) { c1 = __ldg(&it.cpw[i + 3 * EV_T]); n1 = __ldg(&it.nsd[i + 3 * EV_T]); }
+    unary_accumulate<WANT_JAC, JAC_KIND>(ca, na, M, t, F, ep, acc);
+    if (has_b) unary_accumulate<WANT_JAC, JAC_KIND>(cb, nb, M, t, F, ep, acc);
   }
 
   // block reduction

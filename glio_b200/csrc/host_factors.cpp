@@ -42,16 +42,18 @@ struct BandAdder { double* a; int hb; inline void operator()(int i, int j, doubl
 template <class Adder>
 inline void accumulate(int m, const double* r, int nb, const int* off, const int* width, const double* const* J /*m x width[b]*/,
                        const Adder& add, double* g) {
-  for (int a = 0; a < nb; ++a) {
-    for (int p = 0; p < width[a]; ++p) {
-      double gp = 0;
-      for (int k = 0; k < m; ++k) gp += J[a][k * width[a] + p] * r[k];
-      g[off[a] + p] += gp;
-      for (int b = 0; b < nb; ++b) for (int q = 0; q < width[b]; ++q) {
-        double h = 0;
-        for (int k = 0; k < m; ++k) h += J[a][k * width[a] + p] * J[b][k * width[b] + q];
-        add(off[a] + p, off[b] + q, h);
+  // row by row over the non-zeros only (the factor Jacobians are mostly 3x3 blocks and diagonals)
+  int col[64]; double val[64];
+  for (int k = 0; k < m; ++k) {
+    int nz = 0;
+    for (int b = 0; b < nb; ++b)
+      for (int p = 0; p < width[b]; ++p) {
+        const double v = J[b][k * width[b] + p];
+        if (v != 0.0 && nz < 64) { col[nz] = off[b] + p; val[nz] = v; ++nz; }
       }
+    for (int i = 0; i < nz; ++i) {
+      g[col[i]] += val[i] * r[k];
+      for (int j = 0; j < nz; ++j) add(col[i], col[j], val[i] * val[j]);
     }
   }
 }

@@ -188,6 +188,15 @@ int glio_window_solve(glio_ctx* ctx, int W, double* poses, double* speed_bias, g
                       const glio_solver_options* options, glio_solver_summary* summary, glio_iteration* iter_log, int iter_cap,
                       double* step_log, int64_t step_cap);
 
+/* Same solve with the host factors accumulating straight into LOWER-BAND storage (entry (i,j), i-hb <= j <= i, at
+ * Hband[i*(hb+1) + (j-i+hb)]): no dense n x n scratch.  half_bandwidth must cover every coupling the host factors create
+ * (window: prior + IMU chain -> 2*nt-1 = 29 with speed-bias states); < 5 means dense. */
+typedef int (*glio_host_factors_band_fn)(void* user, int K, const double* poses, const double* speed_bias, int want_jac,
+                                         double* Hband, int hb, double* g, double* cost);
+int glio_window_solve_band(glio_ctx* ctx, int W, double* poses, double* speed_bias, glio_host_factors_band_fn host_factors,
+                           int half_bandwidth, void* user, const glio_solver_options* options, glio_solver_summary* summary,
+                           glio_iteration* iter_log, int iter_cap, double* step_log, int64_t step_cap);
+
 /* ---- stand-in host factors (CPU C++, analytic) with the block structure of the reference's non-LiDAR factors:
  * prior 15x[t,q,sb] (marginalisation-prior-like), between 15x[t,q,sb|t,q,sb] (IMU-chain-like), range 1x[t,q]
  * (pseudorange-like).  glio_hf_evaluate has the glio_host_factors_fn signature (user = the set).  They exist so the
@@ -249,8 +258,6 @@ int glio_eval_edge(glio_ctx* ctx, int W, const double* poses_body, double* H, do
  * block-banded (half bandwidth (max|cur-oth|+1)*nt - 1) and stored/factored in band form.  Host factors (IMU chain,
  * delta_q, DD pseudorange: host C++ by design) accumulate into the same LOWER-BAND storage:
  * entry (i,j), i-hb <= j <= i, lives at Hband[i*(hb+1) + (j-i+hb)]. */
-typedef int (*glio_host_factors_band_fn)(void* user, int K, const double* poses, const double* speed_bias, int want_jac,
-                                         double* Hband, int hb, double* g, double* cost);
 int glio_hf_evaluate_band(void* user, int K, const double* poses, const double* speed_bias, int want_jac, double* Hband, int hb,
                           double* g, double* cost);
 int glio_batch_solve(glio_ctx* ctx, int K, double* poses, double* speed_bias, glio_host_factors_band_fn host_factors, void* user,

@@ -68,5 +68,9 @@ def test_window_solve_matches_oracle(oracle, use_sb, n_sel, fuse):
         assert np.max(np.abs(rg["poses"] - ro["poses"])) <= 1e-6
         # it actually optimised something
         assert sg.final_cost < 0.5 * sg.initial_cost
+        # band-storage variant of the host callback: same iterates
+        rb = ctx.window_solve(P["poses_init"], sb0, hf, api.default_solver_options(fuse_candidate_jacobian=fuse), band=29 if use_sb else 11)
+        assert rb["summary"].num_iterations == sg.num_iterations
+        assert np.max(np.abs(rb["poses"] - rg["poses"])) <= 1e-12
     finally:
         ctx.close()
