@@ -110,7 +110,10 @@ struct SearchArgs {
   float gate_sq;
   int32_t* knn_idx;     // [5][Qt] sorted order
   float* knn_sqd;       // [5][Qt] sorted order
-  unsigned long long* n_fallback;
+  unsigned long long* n_fallback;   // statistics: queries deferred to the single-query pass
+  int tile_rings;                   // rings the tile pass may scan before it defers a query (1)
+  uint32_t* deferred;               // sorted positions of deferred queries
+  unsigned int* n_deferred;
 };
 
 __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
@@ -141,7 +144,9 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
     const bool part = !done && cy == lcy && cz == lcz && cx >= lcx && cx < lcx + KNN_SPAN_MAX;
     const int hix = __reduce_max_sync(0xffffffffu, part ? cx : lcx);
     bool unproven = part;
-    for (int r = 1; r <= rmax; ++r) {
+    bool defer = false;
+    const int rlim = min(rmax, a.tile_rings);
+    for (int r = 1; r <= rlim; ++r) {
       const int xa = lcx - r, xb = hix + r;                 // scanned cell range in x after this ring
       const int x0 = max(xa, 0), x1 = min(xb, G.nx - 1);
       const int z0 = max(lcz - r, 0), z1 = min(lcz + r, G.nz - 1);
@@ -206,21 +211,167 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
         if (lcz + r < G.nz - 1)   b = fminf(b, (G.oz + (float)(lcz + r + 1) * G.cell) - qz);
         const float bs = b * 0.999f - 2e-3f;   // safety: float rounding of cell assignment / face positions
         if ((b == INF) || (bs > 0.f && key_dist(t.k4) <= bs * bs)) unproven = false;
-        else ++extra_rings;
+        else if (r == rlim && rlim < rmax) defer = true;      // not provable inside the tile: single-query pass
       }
       if (!__ballot_sync(0xffffffffu, unproven)) break;
     }
     if (part) done = true;
+    // warp-aggregated append of the deferred queries
+    const unsigned dm = __ballot_sync(0xffffffffu, defer);
+    if (dm) {
+      unsigned int base = 0;
+      if (lane == 0) { base = atomicAdd(a.n_deferred, (unsigned int)__popc(dm)); extra_rings += __popc(dm); }
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (defer) a.deferred[base + __popc(dm & ((1u << lane) - 1u))] = (uint32_t)p;
+    }
   }
-  if (a.n_fallback) {
-    for (int o = 16; o > 0; o >>= 1) extra_rings += __shfl_xor_sync(0xffffffffu, extra_rings, o);
-    if (lane == 0 && extra_rings) atomicAdd(a.n_fallback, extra_rings);
-  }
+  if (a.n_fallback && lane == 0 && extra_rings) atomicAdd(a.n_fallback, extra_rings);
   if (active) {
     a.knn_idx[0 * a.Qt + p] = key_idx(t.k0); a.knn_idx[1 * a.Qt + p] = key_idx(t.k1); a.knn_idx[2 * a.Qt + p] = key_idx(t.k2);
     a.knn_idx[3 * a.Qt + p] = key_idx(t.k3); a.knn_idx[4 * a.Qt + p] = key_idx(t.k4);
     a.knn_sqd[0 * a.Qt + p] = key_dist(t.k0); a.knn_sqd[1 * a.Qt + p] = key_dist(t.k1); a.knn_sqd[2 * a.Qt + p] = key_dist(t.k2);
     a.knn_sqd[3 * a.Qt + p] = key_dist(t.k3); a.knn_sqd[4 * a.Qt + p] = key_dist(t.k4);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1a (per-thread variant): one query per thread, rings of cells around the query's own cell, each (y,z) row of a
+// ring is one contiguous range of the sorted map.  Fewer candidate evaluations per query than the tile pass (the
+// searched box is exactly the query's own), at the price of divergent trip counts.  Queries arrive cell-sorted, so
+// the loads of neighbouring threads hit the same lines.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scan_range_keys(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz, Top5& t) {
+  for (int k = s; k < e; ++k) {
+    const float4 p = __ldg(&pts[k]);
+    top5_push(t, l2_simple(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+  }
+}
+
+__global__ void __launch_bounds__(128) k_knn_thread(SearchArgs a) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.Qt) return;
+  const GridDesc& g = a.grid;
+  const float INF = __int_as_float(0x7f800000);
+  const float4 q4 = a.pm[a.order[p]];
+  const float qx = q4.x, qy = q4.y, qz = q4.z;
+  Top5 t; top5_init(t);
+  const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
+  const int rmax = (int)ceilf((sqrtf(a.gate_sq) + 2e-3f) * g.inv_cell) + 1;
+  const bool far_out = cx < -rmax || cy < -rmax || cz < -rmax || cx >= g.nx + rmax || cy >= g.ny + rmax || cz >= g.nz + rmax;
+  const int* __restrict__ cs = g.cell_start;
+  for (int r = 1; r <= rmax && !far_out; ++r) {
+    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.nz - 1);
+    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.ny - 1);
+    const int xa = cx - r, xb = cx + r;
+    const int x0 = max(xa, 0), x1 = min(xb, g.nx - 1);
+    for (int z = z0; z <= z1; ++z) {
+      const bool zshell = (z == cz - r) || (z == cz + r);
+      for (int y = y0; y <= y1; ++y) {
+        const int row = (z * g.ny + y) * g.nx;
+        const bool shell = r == 1 || zshell || (y == cy - r) || (y == cy + r);
+        if (shell) {
+          if (x0 <= x1) scan_range_keys(g.pts, __ldg(&cs[row + x0]), __ldg(&cs[row + x1 + 1]), qx, qy, qz, t);
+        } else {
+          if (xa >= 0 && xa < g.nx) scan_range_keys(g.pts, __ldg(&cs[row + xa]), __ldg(&cs[row + xa + 1]), qx, qy, qz, t);
+          if (xb >= 0 && xb < g.nx) scan_range_keys(g.pts, __ldg(&cs[row + xb]), __ldg(&cs[row + xb + 1]), qx, qy, qz, t);
+        }
+      }
+    }
+    float b = INF;
+    if (cx - r > 0)        b = fminf(b, qx - (g.ox + (float)(cx - r) * g.cell));
+    if (cx + r < g.nx - 1) b = fminf(b, (g.ox + (float)(cx + r + 1) * g.cell) - qx);
+    if (cy - r > 0)        b = fminf(b, qy - (g.oy + (float)(cy - r) * g.cell));
+    if (cy + r < g.ny - 1) b = fminf(b, (g.oy + (float)(cy + r + 1) * g.cell) - qy);
+    if (cz - r > 0)        b = fminf(b, qz - (g.oz + (float)(cz - r) * g.cell));
+    if (cz + r < g.nz - 1) b = fminf(b, (g.oz + (float)(cz + r + 1) * g.cell) - qz);
+    if (b == INF) break;
+    const float bs = b * 0.999f - 2e-3f;
+    if (bs > 0.f && key_dist(t.k4) <= bs * bs) break;
+  }
+  a.knn_idx[0 * a.Qt + p] = key_idx(t.k0); a.knn_idx[1 * a.Qt + p] = key_idx(t.k1); a.knn_idx[2 * a.Qt + p] = key_idx(t.k2);
+  a.knn_idx[3 * a.Qt + p] = key_idx(t.k3); a.knn_idx[4 * a.Qt + p] = key_idx(t.k4);
+  a.knn_sqd[0 * a.Qt + p] = key_dist(t.k0); a.knn_sqd[1 * a.Qt + p] = key_dist(t.k1); a.knn_sqd[2 * a.Qt + p] = key_dist(t.k2);
+  a.knn_sqd[3 * a.Qt + p] = key_dist(t.k3); a.knn_sqd[4 * a.Qt + p] = key_dist(t.k4);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1a': single-query pass for the few queries the tile pass could not prove within its first ring (their 5th
+// neighbour is farther than one cell: sparse map, or a query displaced from the surface by the pose error).
+// One warp per query: the 32 lanes each test one candidate of a batch; the replicated top-5 is updated with the
+// survivors in lane order (uniform control flow).  Rings are scanned from scratch, segment bounds of a whole ring
+// are fetched by the lanes in parallel (one latency per ring instead of one per row), empty segments are skipped.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_knn_deferred(SearchArgs a) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
+  const unsigned int nd = *a.n_deferred;
+  const GridDesc& G = a.grid;
+  const float INF = __int_as_float(0x7f800000);
+  const int* __restrict__ cs = G.cell_start;
+  const int rmax = (int)ceilf((sqrtf(a.gate_sq) + 2e-3f) * G.inv_cell) + 1;
+  for (unsigned int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < nd; it += nwarps) {
+    const int64_t p = a.deferred[it];
+    const float4 q4 = a.pm[a.order[p]];
+    const float qx = q4.x, qy = q4.y, qz = q4.z;
+    const int cx = cell_coord(qx, G.ox, G.inv_cell), cy = cell_coord(qy, G.oy, G.inv_cell), cz = cell_coord(qz, G.oz, G.inv_cell);
+    Top5 t; top5_init(t);
+    for (int r = 1; r <= rmax; ++r) {
+      // segments of ring r: every row (dy,dz) of the (2r+1)^2 square; shell rows span [cx-r, cx+r], inner rows only the
+      // two end cells.  Segment index = row * 2 + part.
+      const int side = 2 * r + 1, nseg = side * side * 2;
+      for (int sb = 0; sb < nseg; sb += 32) {
+        const int sidx = sb + lane;
+        int s = 0, e = 0;
+        if (sidx < nseg) {
+          const int rowi = sidx >> 1, part = sidx & 1;
+          const int dz = rowi / side - r, dy = rowi % side - r;
+          const int z = cz + dz, y = cy + dy;
+          if (z >= 0 && z < G.nz && y >= 0 && y < G.ny) {
+            const bool shell = r == 1 || dz == -r || dz == r || dy == -r || dy == r;
+            const int row = (z * G.ny + y) * G.nx;
+            if (shell) {
+              const int x0 = max(cx - r, 0), x1 = min(cx + r, G.nx - 1);
+              if (part == 0 && x0 <= x1) { s = __ldg(&cs[row + x0]); e = __ldg(&cs[row + x1 + 1]); }
+            } else {
+              const int xc = part == 0 ? cx - r : cx + r;
+              if (xc >= 0 && xc < G.nx) { s = __ldg(&cs[row + xc]); e = __ldg(&cs[row + xc + 1]); }
+            }
+          }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, e > s);
+        while (m) {
+          const int j = __ffs(m) - 1; m &= m - 1;
+          const int ss = __shfl_sync(0xffffffffu, s, j), ee = __shfl_sync(0xffffffffu, e, j);
+          for (int base = ss; base < ee; base += 32) {
+            const int k = base + lane;
+            unsigned long long key = KEY_EMPTY;
+            if (k < ee) { const float4 pt = __ldg(&G.pts[k]); key = make_key(l2_simple(qx, qy, qz, pt.x, pt.y, pt.z), __float_as_int(pt.w)); }
+            unsigned c = __ballot_sync(0xffffffffu, key < t.k4);
+            while (c) {
+              const int l = __ffs(c) - 1; c &= c - 1;
+              const unsigned long long kl = __shfl_sync(0xffffffffu, key, l);
+              if (kl < t.k4) { t.k4 = kl; GLIO_KSWAP(t.k3, t.k4) GLIO_KSWAP(t.k2, t.k3) GLIO_KSWAP(t.k1, t.k2) GLIO_KSWAP(t.k0, t.k1) }
+            }
+          }
+        }
+      }
+      float b = INF;
+      if (cx - r > 0)        b = fminf(b, qx - (G.ox + (float)(cx - r) * G.cell));
+      if (cx + r < G.nx - 1) b = fminf(b, (G.ox + (float)(cx + r + 1) * G.cell) - qx);
+      if (cy - r > 0)        b = fminf(b, qy - (G.oy + (float)(cy - r) * G.cell));
+      if (cy + r < G.ny - 1) b = fminf(b, (G.oy + (float)(cy + r + 1) * G.cell) - qy);
+      if (cz - r > 0)        b = fminf(b, qz - (G.oz + (float)(cz - r) * G.cell));
+      if (cz + r < G.nz - 1) b = fminf(b, (G.oz + (float)(cz + r + 1) * G.cell) - qz);
+      if (b == INF) break;
+      const float bs = b * 0.999f - 2e-3f;
+      if (bs > 0.f && key_dist(t.k4) <= bs * bs) break;
+    }
+    if (lane == 0) {
+      a.knn_idx[0 * a.Qt + p] = key_idx(t.k0); a.knn_idx[1 * a.Qt + p] = key_idx(t.k1); a.knn_idx[2 * a.Qt + p] = key_idx(t.k2);
+      a.knn_idx[3 * a.Qt + p] = key_idx(t.k3); a.knn_idx[4 * a.Qt + p] = key_idx(t.k4);
+      a.knn_sqd[0 * a.Qt + p] = key_dist(t.k0); a.knn_sqd[1 * a.Qt + p] = key_dist(t.k1); a.knn_sqd[2 * a.Qt + p] = key_dist(t.k2);
+      a.knn_sqd[3 * a.Qt + p] = key_dist(t.k3); a.knn_sqd[4 * a.Qt + p] = key_dist(t.k4);
+    }
   }
 }
 
@@ -348,8 +499,15 @@ void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const Assoc
   SearchArgs sa;
   sa.grid = grid; sa.Qt = Qt; sa.pm = w.pm; sa.order = w.order; sa.gate_sq = (float)gates.max_radius;
   sa.knn_idx = w.knn_idx; sa.knn_sqd = w.knn_sqd; sa.n_fallback = w.n_fallback;
+  sa.tile_rings = w.tile_rings; sa.deferred = w.deferred; sa.n_deferred = w.n_deferred;
+  GLIO_CUDA_TRY(cudaMemsetAsync(w.n_deferred, 0, sizeof(unsigned int), st));
   const unsigned ns = (unsigned)((Qt + 32 * KNN_WARPS - 1) / (32 * KNN_WARPS));
-  lc.begin("k_knn_search", st); k_knn_search<<<ns, 32 * KNN_WARPS, 0, st>>>(sa); lc.end(st);
+  if (w.knn_mode == 1) {
+    lc.begin("k_knn_thread", st); k_knn_thread<<<(unsigned)((Qt + 127) / 128), 128, 0, st>>>(sa); lc.end(st);
+  } else {
+    lc.begin("k_knn_search", st); k_knn_search<<<ns, 32 * KNN_WARPS, 0, st>>>(sa); lc.end(st);
+    if (w.tile_rings < 32) { lc.begin("k_knn_deferred", st); k_knn_deferred<<<148 * 8, 128, 0, st>>>(sa); lc.end(st); }
+  }
   FitArgs fa;
   fa.Qt = Qt; fa.pm = w.pm; fa.order = w.order; fa.knn_idx = w.knn_idx; fa.knn_sqd = w.knn_sqd; fa.gates = gates;
   fa.pts_by_idx = gb.tmp4.p; fa.oth_local = oth_local; fa.oth_stride = oth_stride;

@@ -1,6 +1,7 @@
 // capi.cu — the extern "C" boundary (include/glio_b200.h) and the context that owns device state.
 // No CPU fallback: without a CUDA device glio_create fails.
 #include <array>
+#include <chrono>
 #include <map>
 #include <memory>
 
@@ -47,7 +48,7 @@ struct glio_ctx {
   LaunchCounter lc;
 
   int eval_slots = 296;        // resident evaluation blocks: 2 per SM (set from the device at creation)
-  float pts_per_cell = 16.0f;   // target points per occupied grid cell (tuning hook: env GLIO_PTS_PER_CELL)
+  float pts_per_cell = 8.0f;   // target points per occupied grid cell (tuning hook: env GLIO_PTS_PER_CELL)
   GridBuild map;
   bool has_map = false;
   DevBuf<float> map_stage;
@@ -85,6 +86,9 @@ struct glio_ctx {
   DevBuf<int32_t> w_idx5;
   DevBuf<float> w_sqd5;
   DevBuf<int32_t> w_knn_idx;
+  DevBuf<uint32_t> w_deferred;
+  int tile_rings = 64;         // tuning hook: env GLIO_TILE_RINGS (>= 32: the tile pass scans all rings itself)
+  int knn_mode = 1;            // 1: one query per thread (default, fastest measured); 0: warp-cooperative tile pass (env GLIO_KNN_MODE)
   DevBuf<float> w_knn_sqd;
   DevBuf<unsigned long long> d_stats;
   DevBuf<int> w_flags, w_pos, cell_count, cell_pos, scan_tmp;
@@ -114,6 +118,13 @@ struct glio_ctx {
 };
 
 namespace {
+
+// GLIO_TRACE=1: wall-clock marks of the association call (each mark synchronises the stream first)
+struct Trace {
+  bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0; const char* what;
+  Trace(cudaStream_t s, const char* w) : on(getenv("GLIO_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()), what(w) {}
+  void mark(const char* label) { if (!on) return; cudaStreamSynchronize(st); fprintf(stderr, "[glio trace] %s %-18s %8.1f us\n", what, label, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count()); }
+};
 
 thread_local std::string tl_err;
 
@@ -148,7 +159,7 @@ void ensure_work(glio_ctx* c, int64_t Qt, bool pair) {
   c->w_pm.reserve((size_t)Qt); c->w_seg.reserve((size_t)Qt); c->w_order.reserve((size_t)Qt);
   c->w_status.reserve((size_t)Qt); c->w_weight.reserve((size_t)Qt);
   c->w_flags.reserve((size_t)Qt + 1); c->w_pos.reserve((size_t)Qt + 1);
-  c->w_knn_idx.reserve((size_t)Qt * 5); c->w_knn_sqd.reserve((size_t)Qt * 5);
+  c->w_knn_idx.reserve((size_t)Qt * 5); c->w_knn_sqd.reserve((size_t)Qt * 5); c->w_deferred.reserve((size_t)Qt);
   if (!c->d_stats.p) { c->d_stats.reserve(4); GLIO_CUDA_TRY(cudaMemsetAsync(c->d_stats.p, 0, 4 * sizeof(unsigned long long), c->st)); }
   if (pair) c->w_nc.reserve((size_t)Qt * 6); else c->w_nsd.reserve((size_t)Qt);
   if (c->prm.keep_debug) { c->w_idx5.reserve((size_t)Qt * 5); c->w_sqd5.reserve((size_t)Qt * 5); c->w_plane.reserve((size_t)Qt * 4); }
@@ -158,6 +169,7 @@ AssocWork make_work(glio_ctx* c, int64_t Qt, bool pair) {
   AssocWork w{};
   w.Qt = Qt; w.pm = c->w_pm.p; w.seg = c->w_seg.p; w.order = c->w_order.p; w.status = c->w_status.p;
   w.knn_idx = c->w_knn_idx.p; w.knn_sqd = c->w_knn_sqd.p; w.n_fallback = c->d_stats.p;
+  w.knn_mode = c->knn_mode; w.tile_rings = c->tile_rings; w.deferred = c->w_deferred.p; w.n_deferred = reinterpret_cast<unsigned int*>(c->d_stats.p + 2);
   w.nsd = pair ? nullptr : c->w_nsd.p; w.weight = c->w_weight.p; w.normal_cent = pair ? c->w_nc.p : nullptr;
   if (c->prm.keep_debug) { w.idx5 = c->w_idx5.p; w.sqd5 = c->w_sqd5.p; w.plane = c->w_plane.p; }
   return w;
@@ -167,6 +179,7 @@ AssocWork make_work(glio_ctx* c, int64_t Qt, bool pair) {
 void associate_slots(glio_ctx* c, const std::vector<int>& ids, const std::vector<std::array<double, 7>>& lidar_poses,
                      int64_t* n_match) {
   GLIO_REQUIRE(c->has_map, GLIO_ERR_STATE, "glio_set_map must be called before association");
+  Trace tr(c->st, "associate");
   const int nseg = (int)ids.size();
   std::vector<SegDesc> segs(nseg);
   std::vector<CompactDst> dst(nseg);
@@ -188,8 +201,11 @@ void associate_slots(glio_ctx* c, const std::vector<int>& ids, const std::vector
   GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_dst.p, dst.data(), nseg * sizeof(CompactDst), cudaMemcpyHostToDevice, c->st));
   AssocWork w = make_work(c, Qt, false);
   AssocGates gates{c->prm.kd_max_radius, c->prm.surf_dist_thres, c->prm.weight_min};
+  tr.mark("setup+h2d");
   assoc_run(c->map, c->d_segs.p, nseg, w, gates, nullptr, 0, c->cell_count, c->cell_pos, c->scan_tmp, c->st, c->lc);
+  tr.mark("assoc_run");
   compact_run(w, c->d_segs.p, nseg, c->w_flags.p, c->w_pos.p, c->scan_tmp, c->d_dst.p, c->d_counts.p, c->st, c->lc);
+  tr.mark("compact");
   GLIO_CUDA_TRY(cudaMemcpyAsync(c->h_counts.p, c->d_counts.p, nseg * sizeof(int), cudaMemcpyDeviceToHost, c->st));
   if (c->prm.keep_debug) {
     for (int s = 0; s < nseg; ++s) {
@@ -211,6 +227,7 @@ void associate_slots(glio_ctx* c, const std::vector<int>& ids, const std::vector
     if (n_match) n_match[s] = sl.n_match;
   }
   c->items_dirty = true;
+  tr.mark("done");
 }
 
 void build_items(glio_ctx* c, int W) {
@@ -319,6 +336,8 @@ int glio_create(int device, const glio_params* params, glio_ctx** out) {
     c = new glio_ctx();
     c->device = device;
     if (params) c->prm = *params; else glio_default_params(&c->prm);
+    if (const char* e = getenv("GLIO_KNN_MODE")) c->knn_mode = atoi(e) == 0 ? 0 : 1;
+    if (const char* e = getenv("GLIO_TILE_RINGS")) { const int v = atoi(e); if (v >= 1 && v < 64) c->tile_rings = v; }
     if (const char* e = getenv("GLIO_PTS_PER_CELL")) { const float v = (float)atof(e); if (v > 0.1f && v < 1000.f) c->pts_per_cell = v; }
     GLIO_CUDA_TRY(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     { int sms = 148; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->eval_slots = 2 * sms; }
@@ -343,7 +362,7 @@ void glio_destroy(glio_ctx* c) {
   c->cell_count.release(); c->cell_pos.release(); c->scan_tmp.release(); c->d_segs.release(); c->d_dst.release(); c->d_counts.release();
   c->h_counts.release(); c->d_bad.release(); c->d_keep.release(); c->d_items.release(); c->d_kf_item_start.release();
   c->d_partials.release(); c->d_out.release(); c->d_poses.release(); c->d_r.release(); c->d_J.release(); c->h_out.release();
-  c->h_poses.release(); c->d_ticket.release(); c->w_knn_idx.release(); c->w_knn_sqd.release(); c->d_stats.release();
+  c->h_poses.release(); c->d_ticket.release(); c->w_knn_idx.release(); c->w_knn_sqd.release(); c->d_stats.release(); c->w_deferred.release();
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
@@ -364,6 +383,8 @@ int glio_profile_enable(glio_ctx* c, int on) {
     for (auto& r : c->lc.recs) { c->lc.pool.push_back(r.a); c->lc.pool.push_back(r.b); }
     c->lc.recs.clear();
     c->lc.prof = on != 0;
+    // events are created up front: cudaEventCreate inside the timed region would distort what is being measured
+    if (on) while (c->lc.pool.size() < 16384) { cudaEvent_t e; GLIO_CUDA_TRY(cudaEventCreate(&e)); c->lc.pool.push_back(e); }
   });
 }
 

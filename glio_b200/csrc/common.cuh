@@ -108,7 +108,11 @@ struct AssocWork {
   uint32_t* order;      // queries sorted by grid cell
   int32_t* knn_idx;     // [5][Qt] neighbour indices, sorted order (K1a -> K1b)
   float* knn_sqd;       // [5][Qt] squared distances, sorted order
-  unsigned long long* n_fallback;  // statistics: queries that needed the per-thread ring search
+  unsigned long long* n_fallback;  // statistics: queries deferred from the tile pass to the single-query pass
+  int tile_rings;       // rings scanned by the tile pass before deferring (>= 32: never defer)
+  int knn_mode;         // 0: warp-cooperative tile pass, 1: one query per thread
+  uint32_t* deferred;   // [Qt] sorted positions of deferred queries
+  unsigned int* n_deferred;
   uint8_t* status;
   float4* nsd;          // weight*n, weight*d   (scan-to-map)
   float* weight;
