@@ -43,43 +43,54 @@ def host_factor_spec(P, rng):
     return spec
 
 
-def start_clock_sampler(dev_index):
-    f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False); f.close()
-    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    try:
-        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(dev_index)],
-                             stdout=open(f.name, "w"), stderr=subprocess.DEVNULL)
-    except Exception:
-        return None, f.name
-    return p, f.name
+class ClockSampler:
+    """Samples SM clock / throttle reasons DURING the timed region through NVML from a background thread (a polling
+    `nvidia-smi -lms` subprocess was measured to stall kernel launches by milliseconds; NVML reads are microseconds)."""
 
-
-def stop_clock_sampler(p, path):
-    out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
-    if p is not None:
-        p.terminate()
+    def __init__(self, dev_index, period_s=0.004):
+        import threading
+        self.samples = []; self.reasons = set(); self.max_mhz = None; self.ok = False
+        self._stop = threading.Event(); self._period = period_s
         try:
-            p.wait(timeout=5)
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; map through the UUID-less simple case (same order) used on these boxes
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[dev_index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else dev_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
         except Exception:
-            p.kill()
-    try:
-        rows = [r.strip().split(",") for r in open(path) if r.strip()]
-        sm = [float(r[1]) for r in rows if len(r) >= 9]
-        if sm:
-            out["sm_mhz"] = float(np.median(sm)); out["sm_max_mhz"] = float(rows[0][2])
-            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-            for k, nm in enumerate(names):
-                if any("Active" == r[5 + k].strip() and "Not" not in r[5 + k] for r in rows if len(r) >= 9):
-                    out["reasons"].append(nm)
-            out["samples"] = len(sm)
-    except Exception:
-        pass
-    try:
-        os.unlink(path)
-    except Exception:
-        pass
-    return out
+            self.ok = False
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self._nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self._period)
+
+    def start(self):
+        if self.ok:
+            self._t.start()
+
+    def stop(self):
+        if self.ok:
+            self._stop.set(); self._t.join(timeout=2)
+        return dict(sm_mhz=float(np.median(self.samples)) if self.samples else None, sm_max_mhz=self.max_mhz,
+                    reasons=sorted(self.reasons), samples=len(self.samples), how="NVML thread, sampled inside the timed region")
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -196,14 +207,15 @@ def run_glio(args, rank, world, local_rank):
             dist.barrier()
         return iters, ms, wall
 
-    sampler, spath = start_clock_sampler(local_rank) if rank == 0 else (None, None)
     for _ in range(max(args.warmup, 3)):
         one_step(dmap, dscans)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler: sampler.start()
     # (A) the reported value: K steps, inputs resident in HBM, no per-kernel instrumentation
     l0 = ctx.launch_count
     iters, ms, wall = timed_run(dmap, dscans, args.steps)
     launches = ctx.launch_count - l0
-    clocks = stop_clock_sampler(sampler, spath) if rank == 0 else None
+    clocks = sampler.stop() if sampler else None
     # (B) the same K steps again with every kernel launch bracketed by CUDA events on the launching stream: the
     #     per-kernel durations the roofline uses (its step time is reported next to the value for transparency)
     ctx.lib_profile(True)
