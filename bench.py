@@ -44,53 +44,46 @@ def host_factor_spec(P, rng):
 
 
 class ClockSampler:
-    """Samples SM clock / throttle reasons DURING the timed region through NVML from a background thread (a polling
-    `nvidia-smi -lms` subprocess was measured to stall kernel launches by milliseconds; NVML reads are microseconds)."""
+    """SM clock / throttle reasons sampled DURING the timed region through NVML, from the timing thread itself at step
+    boundaries (every few steps; one read costs tens of microseconds and is inside the timed region).  Polling from
+    outside — an `nvidia-smi -lms` subprocess or a concurrent NVML thread — was measured to stall this workload's
+    many short launches by milliseconds per step."""
 
-    def __init__(self, dev_index, period_s=0.004):
-        import threading
+    def __init__(self, dev_index):
         self.samples = []; self.reasons = set(); self.max_mhz = None; self.ok = False
-        self._stop = threading.Event(); self._period = period_s
         try:
             import pynvml
             pynvml.nvmlInit()
             self._nv = pynvml
-            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; map through the UUID-less simple case (same order) used on these boxes
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
             phys = int(vis.split(",")[dev_index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else dev_index
             self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            nv = pynvml
+            self._names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                           "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                           "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                           "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
             self.ok = True
         except Exception:
             self.ok = False
-        self._t = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
-        nv = self._nv
-        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-        while not self._stop.is_set():
-            try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-            except Exception:
-                pass
-            self._stop.wait(self._period)
+    def sample(self):
+        if not self.ok:
+            return
+        try:
+            nv = self._nv
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+            for k, bit in self._names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
 
-    def start(self):
-        if self.ok:
-            self._t.start()
-
-    def stop(self):
-        if self.ok:
-            self._stop.set(); self._t.join(timeout=2)
+    def result(self):
         return dict(sm_mhz=float(np.median(self.samples)) if self.samples else None, sm_max_mhz=self.max_mhz,
-                    reasons=sorted(self.reasons), samples=len(self.samples), how="NVML thread, sampled inside the timed region")
+                    reasons=sorted(self.reasons), samples=len(self.samples), how="NVML, read inside the timed region at step boundaries")
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -186,19 +179,22 @@ def run_glio(args, rank, world, local_rank):
         r = ctx.window_solve(P["poses_init"], sb0, hf, opts, band=29)
         return len(r["steps"]), r
 
-    def timed_run(m, scans, nsteps):
+    def timed_run(m, scans, nsteps, sampler=None):
         iters = 0
+        every = max(1, nsteps // 8)
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(st)
-        for _ in range(nsteps):
+        for si in range(nsteps):
             with torch.cuda.stream(st):
                 flush.fill_(1)                      # L2 flush between steps (256 MB > 126 MB L2), inside the timed region
-            it, _ = one_step(m, scans)
+            it, _r = one_step(m, scans)
             iters += it
+            if sampler is not None and si % every == 0:
+                sampler.sample()
         e1.record(st)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -210,12 +206,11 @@ def run_glio(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         one_step(dmap, dscans)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler: sampler.start()
     # (A) the reported value: K steps, inputs resident in HBM, no per-kernel instrumentation
     l0 = ctx.launch_count
-    iters, ms, wall = timed_run(dmap, dscans, args.steps)
+    iters, ms, wall = timed_run(dmap, dscans, args.steps, sampler)
     launches = ctx.launch_count - l0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.result() if sampler else None
     # (B) the same K steps again with every kernel launch bracketed by CUDA events on the launching stream: the
     #     per-kernel durations the roofline uses (its step time is reported next to the value for transparency)
     ctx.lib_profile(True)

@@ -60,6 +60,65 @@ bool real_roots_deg4(const double* poly5, std::vector<double>* roots) {
   return true;
 }
 
+// dot product with four independent partial sums (a fixed, deterministic association that the compiler can keep in
+// SIMD lanes; the AVX2/FMA clone below is selected at load time on CPUs that have it)
+#define GLIO_DOT4(RES, PA, PB, N)                                             \
+  {                                                                           \
+    double _s0 = 0, _s1 = 0, _s2 = 0, _s3 = 0;                                \
+    int _k = 0;                                                               \
+    for (; _k + 4 <= (N); _k += 4) {                                          \
+      _s0 += (PA)[_k] * (PB)[_k]; _s1 += (PA)[_k + 1] * (PB)[_k + 1];         \
+      _s2 += (PA)[_k + 2] * (PB)[_k + 2]; _s3 += (PA)[_k + 3] * (PB)[_k + 3]; \
+    }                                                                         \
+    for (; _k < (N); ++_k) _s0 += (PA)[_k] * (PB)[_k];                        \
+    (RES) = (_s0 + _s1) + (_s2 + _s3);                                        \
+  }
+
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target_clones("arch=haswell", "default")))
+#endif
+bool cholesky_solve(BandMat& A, const double* b, double* x) {
+  const int n = A.n, hb = A.hb, w = hb + 1;
+  double* a = A.a.data();
+  // right-looking band Cholesky: after column j is scaled, the trailing rows inside the band get a rank-1 update.
+  // The updates are contiguous AXPYs over row segments (SIMD without re-associating any sum).
+  std::vector<double> colv((size_t)hb + 2);
+  double* col = colv.data();
+  for (int j = 0; j < n; ++j) {
+    const double d = a[(size_t)j * w + hb];
+    if (!(d > 0.0) || !std::isfinite(d)) return false;
+    const double l = std::sqrt(d);
+    a[(size_t)j * w + hb] = l;
+    const int m = std::min(hb, n - 1 - j);
+    const double linv = 1.0 / l;                          // one division per column
+    for (int t = 1; t <= m; ++t) {
+      double& e = a[(size_t)(j + t) * w + hb - t];      // A(j+t, j)
+      e *= linv; col[t] = e;
+    }
+    for (int t = 1; t <= m; ++t) {
+      double* __restrict ri = a + (size_t)(j + t) * w + hb - t + 1;  // A(j+t, j+1) ... A(j+t, j+t)
+      const double* __restrict cu = col + 1;
+      const double c = col[t];
+#pragma GCC ivdep
+      for (int u = 0; u < t; ++u) ri[u] -= c * cu[u];
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    const double* ri = a + (size_t)i * w + hb - i;
+    double s = b[i];
+    for (int k = std::max(0, i - hb); k < i; ++k) s -= ri[k] * x[k];
+    x[i] = s / ri[i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = x[i];
+    const int kmax = std::min(n, i + hb + 1);
+    for (int k = i + 1; k < kmax; ++k) s -= a[(size_t)k * w + hb - k + i] * x[k];
+    x[i] = s / a[(size_t)i * w + hb];
+  }
+  for (int i = 0; i < n; ++i) if (!std::isfinite(x[i])) return false;
+  return true;
+}
+
 }  // namespace detail
 
 namespace {

@@ -100,43 +100,9 @@ inline void quat_plus(const double* x, const double* d, double* o) {
   }
 }
 
-// In-place band Cholesky A = L L^T (lower band storage) and solve L L^T x = b.
-// Returns false if a pivot is not positive / finite (Ceres: LINEAR_SOLVER_FAILURE -> mu escalation).
-inline bool cholesky_solve(BandMat& A, const double* b, double* x) {
-  const int n = A.n, hb = A.hb, w = hb + 1;
-  double* a = A.a.data();
-  for (int j = 0; j < n; ++j) {
-    double* rj = a + (size_t)j * w + hb - j;          // rj[k] == A(j,k)
-    const int kj0 = std::max(0, j - hb);
-    double d = rj[j];
-    for (int k = kj0; k < j; ++k) d -= rj[k] * rj[k];
-    if (!(d > 0.0) || !std::isfinite(d)) return false;
-    const double ljj = std::sqrt(d);
-    rj[j] = ljj;
-    const int imax = std::min(n, j + hb + 1);
-    for (int i = j + 1; i < imax; ++i) {
-      double* ri = a + (size_t)i * w + hb - i;
-      const int k0 = std::max(kj0, i - hb);
-      double s = ri[j];
-      for (int k = k0; k < j; ++k) s -= ri[k] * rj[k];
-      ri[j] = s / ljj;
-    }
-  }
-  for (int i = 0; i < n; ++i) {
-    const double* ri = a + (size_t)i * w + hb - i;
-    double s = b[i];
-    for (int k = std::max(0, i - hb); k < i; ++k) s -= ri[k] * x[k];
-    x[i] = s / ri[i];
-  }
-  for (int i = n - 1; i >= 0; --i) {
-    double s = x[i];
-    const int kmax = std::min(n, i + hb + 1);
-    for (int k = i + 1; k < kmax; ++k) s -= a[(size_t)k * w + hb - k + i] * x[k];
-    x[i] = s / a[(size_t)i * w + hb];
-  }
-  for (int i = 0; i < n; ++i) if (!std::isfinite(x[i])) return false;
-  return true;
-}
+// In-place band Cholesky A = L L^T (lower band storage) and solve L L^T x = b (solver.cpp; AVX2/FMA clone picked at
+// load time).  Returns false if a pivot is not positive / finite (Ceres: LINEAR_SOLVER_FAILURE -> mu escalation).
+bool cholesky_solve(BandMat& A, const double* b, double* x);
 
 // real roots of a polynomial of degree <= 4 (highest power first), for the subspace dogleg
 // (dogleg_strategy.cc:421-446 uses FindPolynomialRoots; here: Durand-Kerner + Newton polish in long double).

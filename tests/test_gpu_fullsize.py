@@ -1,0 +1,97 @@
+"""BASELINE.json full sizes (cfg 2: W=20, Q=100k/scan, M=1M; cfg 5: M=1M, Q=100k): the oracle cannot run everything at
+this size in seconds, so parity is checked on samples and through size-independent properties."""
+import numpy as np
+import pytest
+
+from glio_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big(oracle):
+    from glio_b200 import api
+    P = synth.window_problem(W=20, Q=100_000, M=1_000_000, seed=synth.SEED0 + 2)
+    ctx = api.Context(0, keep_debug=1)
+    ctx.set_map(P["map_xyz"])
+    ctx.window_set_scans(P["scans"])
+    nm = ctx.window_associate(P["poses_init"])
+    yield ctx, P, nm
+    ctx.close()
+
+
+def test_full_size_association_matches_oracle_on_whole_scans(big, oracle):
+    """Two complete 100k-point scans against the 1M-point map: every query bit-exact vs the oracle (kd-tree search)."""
+    ctx, P, nm = big
+    tree = oracle.KdTree(P["map_xyz"])
+    for k in (0, 13):
+        t2, q2 = ctx.lidar_pose(P["poses_init"][k])
+        o = oracle.assoc_scan_to_map(P["map_xyz"], P["scans"][k], t2, q2, tree=tree)
+        d = ctx.get_assoc_debug(k, 100_000)
+        assert np.array_equal(d["status"], o["status"])
+        ok = o["status"] != oracle.GO_FAIL_RADIUS
+        assert np.array_equal(d["idx5"][ok], o["idx5"][ok]) and np.array_equal(d["sqd5"][ok], o["sqd5"][ok])
+        assert np.array_equal(d["plane"][ok], o["plane"][ok])
+        assert nm[k] == o["nvalid"]
+        m = ctx.get_matches(k, 100_000)
+        v = o["status"] == oracle.GO_VALID
+        assert np.array_equal(m["nsd"], o["nsd"][v]) and np.array_equal(m["weight"], o["weight"][v])
+        # kNN sortedness (ascending squared distances, as nearestKSearch returns them)
+        assert (np.diff(d["sqd5"][ok], axis=1) >= 0).all()
+
+
+def test_full_size_kd_tree_sample_vs_brute_force(big, oracle):
+    """The oracle's kd-tree itself is checked against brute force on a sample at the full map size."""
+    ctx, P, nm = big
+    rng = np.random.default_rng(0)
+    sel = rng.choice(100_000, 300, replace=False)
+    t2, q2 = ctx.lidar_pose(P["poses_init"][5])
+    pm = oracle.transform_points(P["scans"][5][sel], t2, q2)
+    ib, db, tie = oracle.knn5_brute(P["map_xyz"], pm)
+    d = ctx.get_assoc_debug(5, 100_000)
+    assert not tie.any()
+    near = db[:, 4] < 1.5
+    assert np.array_equal(d["idx5"][sel][near], ib[near]) and np.array_equal(d["sqd5"][sel][near], db[near])
+
+
+def test_full_size_properties(big, oracle):
+    ctx, P, nm = big
+    W = 20
+    assert nm.sum() > 0.9 * W * 100_000
+    full = ctx.eval_unary(P["poses_init"])
+    # idempotence: a second association pass gives the same blocks bit for bit (deterministic reduction order)
+    nm2 = ctx.window_associate(P["poses_init"])
+    again = ctx.eval_unary(P["poses_init"])
+    assert np.array_equal(nm, nm2) and np.array_equal(full["H"], again["H"]) and np.array_equal(full["g"], again["g"]) and np.array_equal(full["cost"], again["cost"])
+    # symmetry / positive semi-definiteness of every 6x6 block, cost-only == cost with Jacobians
+    for k in range(W):
+        assert np.array_equal(full["H"][k], full["H"][k].T)
+        assert np.linalg.eigvalsh(full["H"][k]).min() > -1e-9 * np.abs(full["H"][k]).max()
+    assert np.allclose(ctx.eval_unary(P["poses_init"], want_jac=False)["cost"], full["cost"], rtol=1e-13, atol=0)
+    # linearity in the residual set: selecting a partition of the matches of a slot sums to the full block
+    k = 7
+    n = int(nm[k]); idx = np.arange(n, dtype=np.int32)
+    ctx.select(k, idx[: n // 2]); a = ctx.eval_unary(P["poses_init"])
+    ctx.select(k, idx[n // 2:]); b = ctx.eval_unary(P["poses_init"])
+    ctx.select(k, None)
+    assert np.allclose(a["H"][k] + b["H"][k], full["H"][k], rtol=1e-12, atol=0)
+    assert np.allclose(a["g"][k] + b["g"][k], full["g"][k], rtol=1e-11, atol=1e-9)
+    assert a["cost"][k] + b["cost"][k] == pytest.approx(full["cost"][k], rel=1e-13)
+    assert np.allclose(a["H"][3], full["H"][3], rtol=1e-13, atol=0)     # other slots untouched (work-item boundaries may move)
+    # one slot against the oracle's Jet evaluation (100k residuals, seconds on the CPU)
+    m = ctx.get_matches(k, 100_000)
+    o = oracle.eval_unary(P["poses_init"][k:k + 1], P["q_lb"], P["t_lb"], np.zeros(m["n"], np.int32), m["cp"], m["nsd"],
+                          ctx.params.lidar_const * m["weight"].astype(np.float64), huber_delta=1.0, mode=0, per_residual=False)
+    assert np.max(np.abs(full["H"][k] - o["H"])) <= 1e-11 * np.max(np.abs(o["H"]))
+    assert np.max(np.abs(full["g"][k] - o["g"])) <= 1e-11 * np.max(np.abs(o["g"]))
+    assert full["cost"][k] == pytest.approx(o["cost_total"], rel=1e-12)
+
+
+def test_full_size_solve_decreases_cost_and_is_deterministic(big):
+    ctx, P, nm = big
+    r1 = ctx.window_solve(P["poses_init"])
+    r2 = ctx.window_solve(P["poses_init"])
+    assert np.array_equal(r1["poses"], r2["poses"]) and r1["summary"].num_iterations == r2["summary"].num_iterations
+    costs = [it["cost"] for it in r1["iterations"] if it["step_is_successful"]]
+    assert all(b < a for a, b in zip(costs, costs[1:])) and r1["summary"].final_cost < 0.5 * r1["summary"].initial_cost
+    assert np.allclose(np.linalg.norm(r1["poses"][:, 3:], axis=1), 1.0, atol=1e-12)
