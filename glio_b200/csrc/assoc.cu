@@ -240,10 +240,28 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
 // searched box is exactly the query's own), at the price of divergent trip counts.  Queries arrive cell-sorted, so
 // the loads of neighbouring threads hit the same lines.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void scan_range_keys(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz, Top5& t) {
+// insertion with early exit (a new top-5 entry usually lands near the end); d4f caches the float distance of t.k4
+__device__ __forceinline__ void top5_insert(Top5& t, unsigned long long k) {
+  if (k < t.k3) {
+    t.k4 = t.k3;
+    if (k < t.k2) {
+      t.k3 = t.k2;
+      if (k < t.k1) {
+        t.k2 = t.k1;
+        if (k < t.k0) { t.k1 = t.k0; t.k0 = k; } else t.k1 = k;
+      } else t.k2 = k;
+    } else t.k3 = k;
+  } else t.k4 = k;
+}
+
+__device__ __forceinline__ void scan_range_keys(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz, Top5& t, float& d4f) {
   for (int k = s; k < e; ++k) {
     const float4 p = __ldg(&pts[k]);
-    top5_push(t, l2_simple(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+    const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+    if (d <= d4f) {                                  // cheap float test first; ties on distance resolved on the full key
+      const unsigned long long key = make_key(d, __float_as_int(p.w));
+      if (key < t.k4) { t.k4 = key; GLIO_KSWAP(t.k3, t.k4) GLIO_KSWAP(t.k2, t.k3) GLIO_KSWAP(t.k1, t.k2) GLIO_KSWAP(t.k0, t.k1) d4f = key_dist(t.k4); }
+    }
   }
 }
 
@@ -259,21 +277,24 @@ __global__ void __launch_bounds__(128) k_knn_thread(SearchArgs a) {
   const int rmax = (int)ceilf((sqrtf(a.gate_sq) + 2e-3f) * g.inv_cell) + 1;
   const bool far_out = cx < -rmax || cy < -rmax || cz < -rmax || cx >= g.nx + rmax || cy >= g.ny + rmax || cz >= g.nz + rmax;
   const int* __restrict__ cs = g.cell_start;
+  float d4f = INF;
   for (int r = 1; r <= rmax && !far_out; ++r) {
-    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.nz - 1);
-    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.ny - 1);
     const int xa = cx - r, xb = cx + r;
     const int x0 = max(xa, 0), x1 = min(xb, g.nx - 1);
-    for (int z = z0; z <= z1; ++z) {
-      const bool zshell = (z == cz - r) || (z == cz + r);
-      for (int y = y0; y <= y1; ++y) {
-        const int row = (z * g.ny + y) * g.nx;
-        const bool shell = r == 1 || zshell || (y == cy - r) || (y == cy + r);
-        if (shell) {
-          if (x0 <= x1) scan_range_keys(g.pts, __ldg(&cs[row + x0]), __ldg(&cs[row + x1 + 1]), qx, qy, qz, t);
-        } else {
-          if (xa >= 0 && xa < g.nx) scan_range_keys(g.pts, __ldg(&cs[row + xa]), __ldg(&cs[row + xa + 1]), qx, qy, qz, t);
-          if (xb >= 0 && xb < g.nx) scan_range_keys(g.pts, __ldg(&cs[row + xb]), __ldg(&cs[row + xb + 1]), qx, qy, qz, t);
+    {
+      const int z0 = max(cz - r, 0), z1 = min(cz + r, g.nz - 1);
+      const int y0 = max(cy - r, 0), y1 = min(cy + r, g.ny - 1);
+      for (int z = z0; z <= z1; ++z) {
+        const bool zshell = (z == cz - r) || (z == cz + r);
+        for (int y = y0; y <= y1; ++y) {
+          const int row = (z * g.ny + y) * g.nx;
+          const bool shell = r == 1 || zshell || (y == cy - r) || (y == cy + r);
+          if (shell) {
+            if (x0 <= x1) scan_range_keys(g.pts, __ldg(&cs[row + x0]), __ldg(&cs[row + x1 + 1]), qx, qy, qz, t, d4f);
+          } else {
+            if (xa >= 0 && xa < g.nx) scan_range_keys(g.pts, __ldg(&cs[row + xa]), __ldg(&cs[row + xa + 1]), qx, qy, qz, t, d4f);
+            if (xb >= 0 && xb < g.nx) scan_range_keys(g.pts, __ldg(&cs[row + xb]), __ldg(&cs[row + xb + 1]), qx, qy, qz, t, d4f);
+          }
         }
       }
     }

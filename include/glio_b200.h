@@ -246,6 +246,12 @@ int glio_batch_declare_pairs(glio_ctx* ctx, const int32_t* pairs_cur, const int3
  * (block (cur,oth): row = cur tangent, col = oth tangent, pairs in glio_batch_pair_list order), g[K*6], cost. */
 int glio_eval_binary(glio_ctx* ctx, int K, const double* poses, double* Hdiag, double* Hoff, double* g, double* cost);
 
+/* ---- K3: the marginalisation Schur step of MarginalizationInfo::Marginalize (GLIO/src/MarginalizationFactor.cpp:176-201),
+ * host C++ (123 x 15 x 123 at W = 20: too small for the GPU to matter).  A[n_total x n_total] row-major and b[n_total]
+ * are the dense normal equations with the m states to drop first (LiDAR part: glio_eval_unary with jac_kind = 1);
+ * outputs linearized_jacobians[(n_total-m)^2] row-major and linearized_residuals[n_total-m].  eps = 1e-8 in the reference. */
+int glio_marginalize(const double* A, const double* b, int n_total, int m, double eps, double* lin_jac, double* lin_res);
+
 /* ---- K2e: point-to-edge residuals (LidarEdgeFactor, LidarKeyframeFactor.h:12-70).  The reference defines this factor
  * but never instantiates it and has no edge association, so the correspondences are an input:
  * cp[3n] scan point, pa/pb[3n] two points of the map line, s[n] weight.  Huber(huber_delta) as for the plane factors.
