@@ -290,7 +290,8 @@ def run_glio(args, rank, world, local_rank):
                             parallelism="replicas only (window path does not shard)" if world > 1 else "1 GPU",
                             l2="256 MB flush between steps inside the timed region; per-step working set ~300 MB > 126 MB L2; "
                                "K2 re-reads the 64 MB residual table every iteration as the real solve does",
-                            host_wall_ms_per_step=1e3 * wall / args.steps, ms_per_step_with_kernel_events=ms_prof / args.steps, knn_deferred_queries_per_step=n_fallback / args.steps, wall_split=split, kernels=kern),
+                            host_wall_ms_per_step=1e3 * wall / args.steps, ms_per_step_with_kernel_events=ms_prof / args.steps, knn_deferred_queries_per_step=n_fallback / args.steps, wall_split=split,
+                            solve_split_ms=dict(total=round(1e3 * s.total_seconds, 3), evaluation=round(1e3 * s.eval_seconds, 3), band_cholesky=round(1e3 * s.linear_solver_seconds, 3)), kernels=kern),
                 e2e=dict(value=e2e, unit="iterations/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=tmax_e / args.steps),
                 gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
     print(json.dumps(line))

@@ -254,7 +254,8 @@ class SolverSummary(C.Structure):
     _fields_ = [("termination", C.c_int32), ("num_iterations", C.c_int32), ("num_successful_steps", C.c_int32),
                 ("num_unsuccessful_steps", C.c_int32), ("num_evaluations", C.c_int32), ("num_jacobian_evaluations", C.c_int32),
                 ("num_linear_solves", C.c_int32), ("num_valid_steps", C.c_int32), ("initial_cost", C.c_double),
-                ("final_cost", C.c_double), ("message", C.c_char * 128)]
+                ("final_cost", C.c_double), ("eval_seconds", C.c_double), ("linear_solver_seconds", C.c_double),
+                ("total_seconds", C.c_double), ("message", C.c_char * 128)]
 
 
 HOST_FACTORS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,

@@ -287,6 +287,7 @@ void fill_summary(const SolverSummary& S, int n, glio_solver_summary* summary, g
       summary->num_evaluations = S.num_evaluations; summary->num_jacobian_evaluations = S.num_jacobian_evaluations;
       summary->num_linear_solves = S.num_linear_solves; summary->num_valid_steps = (int)(S.steps.size() / (size_t)n);
       summary->initial_cost = S.initial_cost; summary->final_cost = S.final_cost;
+      summary->eval_seconds = S.eval_seconds; summary->linear_solver_seconds = S.linear_solver_seconds; summary->total_seconds = S.total_seconds;
       snprintf(summary->message, sizeof(summary->message), "%s", S.message.c_str());
     }
     if (iter_log) for (int i = 0; i < (int)S.iterations.size() && i < iter_cap; ++i) {

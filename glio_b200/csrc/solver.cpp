@@ -1,6 +1,7 @@
 // solver.cpp — see solver.h.  Host C++ only (no CUDA): the iteration driver around the device evaluation.
 #include "solver.h"
 
+#include <chrono>
 #include <complex>
 
 namespace glio {
@@ -60,23 +61,6 @@ bool real_roots_deg4(const double* poly5, std::vector<double>* roots) {
   return true;
 }
 
-// dot product with four independent partial sums (a fixed, deterministic association that the compiler can keep in
-// SIMD lanes; the AVX2/FMA clone below is selected at load time on CPUs that have it)
-#define GLIO_DOT4(RES, PA, PB, N)                                             \
-  {                                                                           \
-    double _s0 = 0, _s1 = 0, _s2 = 0, _s3 = 0;                                \
-    int _k = 0;                                                               \
-    for (; _k + 4 <= (N); _k += 4) {                                          \
-      _s0 += (PA)[_k] * (PB)[_k]; _s1 += (PA)[_k + 1] * (PB)[_k + 1];         \
-      _s2 += (PA)[_k + 2] * (PB)[_k + 2]; _s3 += (PA)[_k + 3] * (PB)[_k + 3]; \
-    }                                                                         \
-    for (; _k < (N); ++_k) _s0 += (PA)[_k] * (PB)[_k];                        \
-    (RES) = (_s0 + _s1) + (_s2 + _s3);                                        \
-  }
-
-#if defined(__x86_64__) && defined(__GNUC__)
-__attribute__((target_clones("arch=haswell", "default")))
-#endif
 bool cholesky_solve(BandMat& A, const double* b, double* x) {
   const int n = A.n, hb = A.hb, w = hb + 1;
   double* a = A.a.data();
@@ -157,10 +141,19 @@ struct StepEvaluator {
 
 }  // namespace
 
-void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* sum) {
+void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval_user, SolverSummary* sum) {
   const int n = n_, na = n_amb_;
   SolverSummary& S = *sum;
   S = SolverSummary();
+  typedef std::chrono::steady_clock clk;
+  const auto t_begin = clk::now();
+  auto eval = [&](const double* xx, bool wj, double* cst, BandMat* HH, double* gg) -> bool {
+    const auto t0 = clk::now();
+    const bool ok = eval_user(xx, wj, cst, HH, gg);
+    S.eval_seconds += std::chrono::duration<double>(clk::now() - t0).count();
+    return ok;
+  };
+  struct Fin { SolverSummary& s; clk::time_point t; ~Fin() { s.total_seconds = std::chrono::duration<double>(clk::now() - t).count(); } } fin{S, t_begin};
   std::vector<double> x(x_io, x_io + na), cand(na), proj(na);
   BandMat H, Hs, Hc, A;
   std::vector<double> g(n), gs(n), gc(n);
@@ -298,7 +291,10 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval, SolverSummary* s
       const double sm = std::sqrt(mu);
       for (int i = 0; i < n; ++i) { const double lm = diag[i] * sm; A.at(i, i) += lm * lm; }
       S.num_linear_solves++;
-      if (detail::cholesky_solve(A, gs.data(), y.data())) { ok = true; break; }
+      const auto tl0 = clk::now();
+      const bool chol_ok = detail::cholesky_solve(A, gs.data(), y.data());
+      S.linear_solver_seconds += std::chrono::duration<double>(clk::now() - tl0).count();
+      if (chol_ok) { ok = true; break; }
       mu *= mu_inc;
     }
     if (!ok) return 1;

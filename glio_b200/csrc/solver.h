@@ -64,6 +64,7 @@ struct SolverSummary {
   std::vector<IterationRecord> iterations;
   std::vector<double> steps;   // tangent delta of every iteration that produced a valid step (n each), in order
   int num_evaluations = 0, num_jacobian_evaluations = 0, num_linear_solves = 0;
+  double eval_seconds = 0, linear_solver_seconds = 0, total_seconds = 0;   // wall-clock split (like Ceres' Summary timers)
 };
 
 // Symmetric matrix in lower-band storage: entry (i,j), i-hb <= j <= i, lives at a[i*(hb+1) + (j-i+hb)].
@@ -100,8 +101,7 @@ inline void quat_plus(const double* x, const double* d, double* o) {
   }
 }
 
-// In-place band Cholesky A = L L^T (lower band storage) and solve L L^T x = b (solver.cpp; AVX2/FMA clone picked at
-// load time).  Returns false if a pivot is not positive / finite (Ceres: LINEAR_SOLVER_FAILURE -> mu escalation).
+// In-place band Cholesky A = L L^T (lower band storage) and solve L L^T x = b (solver.cpp, right-looking).  Returns false if a pivot is not positive / finite (Ceres: LINEAR_SOLVER_FAILURE -> mu escalation).
 bool cholesky_solve(BandMat& A, const double* b, double* x);
 
 // real roots of a polynomial of degree <= 4 (highest power first), for the subspace dogleg

@@ -172,6 +172,9 @@ typedef struct {
   int32_t num_successful_steps, num_unsuccessful_steps;
   int32_t num_evaluations, num_jacobian_evaluations, num_linear_solves, num_valid_steps;
   double initial_cost, final_cost;
+  double eval_seconds;                   /* wall clock inside residual/Jacobian evaluation (device kernel + copies + host factors) */
+  double linear_solver_seconds;          /* wall clock inside the band Cholesky solves */
+  double total_seconds;
   char message[128];
 } glio_solver_summary;
 
