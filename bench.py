@@ -257,9 +257,9 @@ def run_glio(args, rank, world, local_rank):
     for name, (tot_ms, cnt) in prof.items():
         kern[name] = dict(ms_total=round(tot_ms, 4), launches=cnt, ms_avg=round(tot_ms / max(cnt, 1), 5))
     roof = None
-    if ("k_knn_search" in prof or "k_knn_thread" in prof) and "k_plane_fit" in prof:
+    if ("k_knn_search" in prof or "k_knn_thread" in prof or "k_knn_box" in prof) and "k_plane_fit" in prof:
         # K1 is one association pass issued as two launches (warp-cooperative search, then the fp64 plane fit)
-        avg_ms = sum(prof[k][0] / prof[k][1] for k in ("k_knn_search", "k_knn_deferred", "k_knn_thread", "k_plane_fit") if k in prof and prof[k][1])
+        avg_ms = sum(prof[k][0] / prof[k][1] for k in ("k_knn_search", "k_knn_deferred", "k_knn_thread", "k_knn_box", "k_plane_fit") if k in prof and prof[k][1])
         alg = 116.0 * Qt + 12.0 * CFG["M"]
         ach = alg / (avg_ms * 1e-3) / 1e9
         roof = dict(bound="hbm", kernel="K1 association pass = k_knn_search + k_knn_deferred + k_plane_fit (exact 5-NN + plane fit + gates)",

@@ -65,7 +65,15 @@ __device__ __forceinline__ float key_dist(unsigned long long k) { return __uint_
 __device__ __forceinline__ int key_idx(unsigned long long k) { return (int)(unsigned int)(k & 0xffffffffull); }
 constexpr unsigned long long KEY_EMPTY = 0x7f8000007fffffffull;   // (+inf, INT_MAX)
 __device__ __forceinline__ void top5_init(Top5& t) { t.k0 = t.k1 = t.k2 = t.k3 = t.k4 = KEY_EMPTY; }
-#define GLIO_KSWAP(A, B) { const unsigned long long _lo = (A) < (B) ? (A) : (B); const unsigned long long _hi = (A) < (B) ? (B) : (A); (A) = _lo; (B) = _hi; }
+// compare-exchange of two keys: one 64-bit compare + select for the smaller key, the larger one by XOR (the plain
+// two-select form made ptxas emit a second, mirrored compare: 8 instead of 6 instructions per exchange in the hottest
+// block of K1a)
+__device__ __forceinline__ void key_cswap(unsigned long long& a, unsigned long long& b) {
+  const unsigned long long lo = a < b ? a : b;
+  b = a ^ b ^ lo;
+  a = lo;
+}
+#define GLIO_KSWAP(A, B) key_cswap((A), (B));
 __device__ __forceinline__ void top5_push(Top5& t, float d, int id) {
   const unsigned long long k = make_key(d, id);
   if (k < t.k4) {
@@ -240,20 +248,6 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
 // searched box is exactly the query's own), at the price of divergent trip counts.  Queries arrive cell-sorted, so
 // the loads of neighbouring threads hit the same lines.
 // ---------------------------------------------------------------------------------------------------
-// insertion with early exit (a new top-5 entry usually lands near the end); d4f caches the float distance of t.k4
-__device__ __forceinline__ void top5_insert(Top5& t, unsigned long long k) {
-  if (k < t.k3) {
-    t.k4 = t.k3;
-    if (k < t.k2) {
-      t.k3 = t.k2;
-      if (k < t.k1) {
-        t.k2 = t.k1;
-        if (k < t.k0) { t.k1 = t.k0; t.k0 = k; } else t.k1 = k;
-      } else t.k2 = k;
-    } else t.k3 = k;
-  } else t.k4 = k;
-}
-
 __device__ __forceinline__ void scan_range_keys(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz, Top5& t, float& d4f) {
   for (int k = s; k < e; ++k) {
     const float4 p = __ldg(&pts[k]);
@@ -265,23 +259,32 @@ __device__ __forceinline__ void scan_range_keys(const float4* __restrict__ pts, 
   }
 }
 
-__global__ void __launch_bounds__(128) k_knn_thread(SearchArgs a) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= a.Qt) return;
-  const GridDesc& g = a.grid;
+// rings [r_lo, r_hi] of one query's search box; returns true when the top-5 is final (proven inside the scanned box,
+// the box covers the grid, or it covers the gate radius) and false when more rings are needed
+__device__ __forceinline__ bool thread_rings(const GridDesc& g, float qx, float qy, float qz, int cx, int cy, int cz, int r_lo, int r_hi, int rmax,
+                                             Top5& t, float& d4f, int* __restrict__ sb = nullptr) {
   const float INF = __int_as_float(0x7f800000);
-  const float4 q4 = a.pm[a.order[p]];
-  const float qx = q4.x, qy = q4.y, qz = q4.z;
-  Top5 t; top5_init(t);
-  const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
-  const int rmax = (int)ceilf((sqrtf(a.gate_sq) + 2e-3f) * g.inv_cell) + 1;
-  const bool far_out = cx < -rmax || cy < -rmax || cz < -rmax || cx >= g.nx + rmax || cy >= g.ny + rmax || cz >= g.nz + rmax;
   const int* __restrict__ cs = g.cell_start;
-  float d4f = INF;
-  for (int r = 1; r <= rmax && !far_out; ++r) {
+  for (int r = r_lo; r <= r_hi; ++r) {
     const int xa = cx - r, xb = cx + r;
     const int x0 = max(xa, 0), x1 = min(xb, g.nx - 1);
-    {
+    if (r == 1 && sb) {
+      // first ring: fetch the bounds of all nine rows up front (18 independent loads in flight instead of nine
+      // dependent load -> scan steps), park them in this thread's shared-memory column, then scan the query's own
+      // row first so the 5th distance tightens early
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int z = cz + i / 3 - 1, y = cy + i % 3 - 1;
+        int s = 0, e = 0;
+        if (z >= 0 && z < g.nz && y >= 0 && y < g.ny && x0 <= x1) { const int row = (z * g.ny + y) * g.nx; s = __ldg(&cs[row + x0]); e = __ldg(&cs[row + x1 + 1]); }
+        sb[(2 * i) * 128] = s; sb[(2 * i + 1) * 128] = e;
+      }
+#pragma unroll 1
+      for (int i = 0; i < 9; ++i) {
+        const int o = (int)((0x862053714ull >> (4 * i)) & 15ull);     // 4,1,7,3,5,0,2,6,8
+        scan_range_keys(g.pts, sb[(2 * o) * 128], sb[(2 * o + 1) * 128], qx, qy, qz, t, d4f);
+      }
+    } else {
       const int z0 = max(cz - r, 0), z1 = min(cz + r, g.nz - 1);
       const int y0 = max(cy - r, 0), y1 = min(cy + r, g.ny - 1);
       for (int z = z0; z <= z1; ++z) {
@@ -305,14 +308,105 @@ __global__ void __launch_bounds__(128) k_knn_thread(SearchArgs a) {
     if (cy + r < g.ny - 1) b = fminf(b, (g.oy + (float)(cy + r + 1) * g.cell) - qy);
     if (cz - r > 0)        b = fminf(b, qz - (g.oz + (float)(cz - r) * g.cell));
     if (cz + r < g.nz - 1) b = fminf(b, (g.oz + (float)(cz + r + 1) * g.cell) - qz);
-    if (b == INF) break;
+    if (b == INF) return true;
     const float bs = b * 0.999f - 2e-3f;
-    if (bs > 0.f && key_dist(t.k4) <= bs * bs) break;
+    if (bs > 0.f && key_dist(t.k4) <= bs * bs) return true;
   }
+  return r_hi >= rmax;
+}
+
+__device__ __forceinline__ void store_top5(const SearchArgs& a, int64_t p, const Top5& t) {
   a.knn_idx[0 * a.Qt + p] = key_idx(t.k0); a.knn_idx[1 * a.Qt + p] = key_idx(t.k1); a.knn_idx[2 * a.Qt + p] = key_idx(t.k2);
   a.knn_idx[3 * a.Qt + p] = key_idx(t.k3); a.knn_idx[4 * a.Qt + p] = key_idx(t.k4);
   a.knn_sqd[0 * a.Qt + p] = key_dist(t.k0); a.knn_sqd[1 * a.Qt + p] = key_dist(t.k1); a.knn_sqd[2 * a.Qt + p] = key_dist(t.k2);
   a.knn_sqd[3 * a.Qt + p] = key_dist(t.k3); a.knn_sqd[4 * a.Qt + p] = key_dist(t.k4);
+}
+
+// K1a (ring growth, knn_mode 1): one query per thread, whole rings until the 5th distance is provably inside the box.
+__global__ void __launch_bounds__(128, 7) k_knn_thread(SearchArgs a) {
+  __shared__ int sbnd[18 * 128];                     // [row bound][thread]: conflict-free columns
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.Qt) return;
+  const GridDesc& g = a.grid;
+  const float4 q4 = a.pm[a.order[p]];
+  const float qx = q4.x, qy = q4.y, qz = q4.z;
+  Top5 t; top5_init(t);
+  const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
+  const int rmax = (int)ceilf((sqrtf(a.gate_sq) + 2e-3f) * g.inv_cell) + 1;
+  const bool far_out = cx < -rmax || cy < -rmax || cz < -rmax || cx >= g.nx + rmax || cy >= g.ny + rmax || cz >= g.nz + rmax;
+  float d4f = __int_as_float(0x7f800000);
+  if (!far_out) thread_rings(g, qx, qy, qz, cx, cy, cz, 1, rmax, rmax, t, d4f, sbnd + threadIdx.x);
+  store_top5(a, p, t);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1a (box growth): the searched box of a query grows one FACE at a time instead of one ring at a time.  After the
+// start box (3x3x3 cells around the query, or only its own cell when start_own) a face is pushed out by one cell
+// layer only if something nearer than the current 5th distance could still hide behind it: the face is not at the
+// grid border, not farther than the gate radius, and closer to the query than the 5th distance.  A query near one
+// cell wall with a 5th neighbour a little beyond it scans one extra slab of 9 cells instead of the 98 cells of a
+// full second ring; the top-5 is exact under the same proof as the ring search (every unscanned point lies beyond
+// some face, all faces are at least the 5th distance away), faces are re-tested with the freshest 5th distance.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scan_rows(const GridDesc& g, int x0, int x1, int y0, int y1, int z0, int z1, float qx, float qy, float qz, Top5& t, float& d4f) {
+  x0 = max(x0, 0); x1 = min(x1, g.nx - 1); y0 = max(y0, 0); y1 = min(y1, g.ny - 1); z0 = max(z0, 0); z1 = min(z1, g.nz - 1);
+  if (x0 > x1) return;
+  const int* __restrict__ cs = g.cell_start;
+  for (int z = z0; z <= z1; ++z)
+    for (int y = y0; y <= y1; ++y) {
+      const int row = (z * g.ny + y) * g.nx;
+      scan_range_keys(g.pts, __ldg(&cs[row + x0]), __ldg(&cs[row + x1 + 1]), qx, qy, qz, t, d4f);
+    }
+}
+
+template <bool START_OWN>
+__global__ void __launch_bounds__(128, 6) k_knn_box(SearchArgs a) {
+  __shared__ int sbnd[18 * 128];
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.Qt) return;
+  const GridDesc& g = a.grid;
+  const float4 q4 = a.pm[a.order[p]];
+  const float qx = q4.x, qy = q4.y, qz = q4.z;
+  Top5 t; top5_init(t);
+  const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
+  const float gate_r = sqrtf(a.gate_sq) + 2e-3f;
+  const int rmax = (int)ceilf(gate_r * g.inv_cell) + 1;
+  const bool far_out = cx < -rmax || cy < -rmax || cz < -rmax || cx >= g.nx + rmax || cy >= g.ny + rmax || cz >= g.nz + rmax;
+  float d4f = __int_as_float(0x7f800000);
+  if (!far_out) {
+    int lx, hx, ly, hy, lz, hz;
+    if (START_OWN) {
+      lx = hx = cx; ly = hy = cy; lz = hz = cz;
+      scan_rows(g, cx, cx, cy, cy, cz, cz, qx, qy, qz, t, d4f);
+    } else {
+      lx = cx - 1; hx = cx + 1; ly = cy - 1; hy = cy + 1; lz = cz - 1; hz = cz + 1;
+      thread_rings(g, qx, qy, qz, cx, cy, cz, 1, 1, rmax, t, d4f, sbnd + threadIdx.x);
+    }
+    for (int round = 0; round < rmax + 3; ++round) {
+      bool any = false;
+#pragma unroll 1
+      for (int f = 0; f < 6; ++f) {
+        const int ax = f >> 1;
+        const bool up = (f & 1) != 0;
+        const int lo = ax == 0 ? lx : (ax == 1 ? ly : lz), hi = ax == 0 ? hx : (ax == 1 ? hy : hz), n = ax == 0 ? g.nx : (ax == 1 ? g.ny : g.nz);
+        const float qa = ax == 0 ? qx : (ax == 1 ? qy : qz), oa = ax == 0 ? g.ox : (ax == 1 ? g.oy : g.oz);
+        if (up ? (hi >= n - 1) : (lo <= 0)) continue;                       // nothing beyond this face
+        const float b = up ? (oa + (float)(hi + 1) * g.cell) - qa : qa - (oa + (float)lo * g.cell);
+        const float bs = b * 0.999f - 2e-3f;
+        if (bs >= gate_r) continue;                                         // beyond the gate radius
+        if (bs > 0.f && key_dist(t.k4) <= bs * bs) continue;                // the 5th distance is inside this face
+        const int nc = up ? hi + 1 : lo - 1;
+        int bx0 = lx, bx1 = hx, by0 = ly, by1 = hy, bz0 = lz, bz1 = hz;
+        if (ax == 0) { bx0 = bx1 = nc; if (up) hx = nc; else lx = nc; }
+        else if (ax == 1) { by0 = by1 = nc; if (up) hy = nc; else ly = nc; }
+        else { bz0 = bz1 = nc; if (up) hz = nc; else lz = nc; }
+        scan_rows(g, bx0, bx1, by0, by1, bz0, bz1, qx, qy, qz, t, d4f);
+        any = true;
+      }
+      if (!any) break;
+    }
+  }
+  store_top5(a, p, t);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -523,7 +617,12 @@ void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const Assoc
   sa.tile_rings = w.tile_rings; sa.deferred = w.deferred; sa.n_deferred = w.n_deferred;
   GLIO_CUDA_TRY(cudaMemsetAsync(w.n_deferred, 0, sizeof(unsigned int), st));
   const unsigned ns = (unsigned)((Qt + 32 * KNN_WARPS - 1) / (32 * KNN_WARPS));
-  if (w.knn_mode == 1) {
+  if (w.knn_mode == 2 || w.knn_mode == 3) {
+    lc.begin("k_knn_box", st);
+    if (w.knn_mode == 3) k_knn_box<true><<<(unsigned)((Qt + 127) / 128), 128, 0, st>>>(sa);
+    else k_knn_box<false><<<(unsigned)((Qt + 127) / 128), 128, 0, st>>>(sa);
+    lc.end(st);
+  } else if (w.knn_mode == 1) {
     lc.begin("k_knn_thread", st); k_knn_thread<<<(unsigned)((Qt + 127) / 128), 128, 0, st>>>(sa); lc.end(st);
   } else {
     lc.begin("k_knn_search", st); k_knn_search<<<ns, 32 * KNN_WARPS, 0, st>>>(sa); lc.end(st);
