@@ -513,8 +513,11 @@ struct FitArgs {
   double* plane;
 };
 
+#ifndef GLIO_FIT_MINBLOCKS
+#define GLIO_FIT_MINBLOCKS 4
+#endif
 template <bool PAIR>
-__global__ void __launch_bounds__(128) k_plane_fit(FitArgs a) {
+__global__ void __launch_bounds__(128, GLIO_FIT_MINBLOCKS) k_plane_fit(FitArgs a) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.Qt) return;
   const int64_t g = a.order[p];

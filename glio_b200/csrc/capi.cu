@@ -1,6 +1,7 @@
 // capi.cu — the extern "C" boundary (include/glio_b200.h) and the context that owns device state.
 // No CPU fallback: without a CUDA device glio_create fails.
 #include <array>
+#include <atomic>
 #include <chrono>
 #include <map>
 #include <memory>
@@ -104,6 +105,8 @@ struct glio_ctx {
   DevBuf<int> d_kf_item_start;
   DevBuf<double> d_partials, d_out, d_poses, d_r, d_J;
   PinnedBuf<double> h_out, h_poses;
+  PinnedBuf<unsigned int> h_flag;      // completion epoch written by the last block of k_eval_unary
+  unsigned int eval_epoch = 0;
   DevBuf<unsigned int> d_ticket;
   bool items_dirty = true;
   int items_W = -1;
@@ -301,14 +304,48 @@ void fill_summary(const SolverSummary& S, int n, glio_solver_summary* summary, g
 }
 
 // device evaluation of all active unary residuals -> c->h_out (W x 28: 21 upper-tri H, 6 g, 1 cost), synchronised
-void eval_unary_blocks(glio_ctx* c, int W, const double* poses_body, int jac_kind, bool want_jac) {
+// launch half: returns the epoch to wait for (0: nothing was launched, h_out already holds zeros)
+unsigned int eval_unary_launch(glio_ctx* c, int W, const double* poses_body, int jac_kind, bool want_jac) {
   build_items(c, W);
+  // Zero-copy round trip: the W poses travel in the kernel parameters, the last block writes the W x 28 result into
+  // pinned host memory and raises an epoch flag the host spins on.  This replaces H2D copy + launch + D2H copy +
+  // stream synchronise on the per-iteration path, and lets the caller evaluate its host factors while the kernel runs.
   memcpy(c->h_poses.p, poses_body, (size_t)W * 7 * sizeof(double));
-  GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_poses.p, c->h_poses.p, (size_t)W * 7 * sizeof(double), cudaMemcpyHostToDevice, c->st));
-  eval_unary_run(c->d_items.p, c->n_items, W, c->d_poses.p, eval_params(c), jac_kind, want_jac, c->d_partials.p, c->d_out.p,
-                 c->d_kf_item_start.p, c->d_ticket.p, c->st, c->lc);
-  GLIO_CUDA_TRY(cudaMemcpyAsync(c->h_out.p, c->d_out.p, (size_t)W * GLIO_NACC * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-  GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+  if (c->n_items <= 0) {
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    memset(c->h_out.p, 0, (size_t)W * GLIO_NACC * sizeof(double));
+    return 0u;
+  }
+  if (!c->h_flag.p) { c->h_flag.reserve(4); memset(c->h_flag.p, 0, 4 * sizeof(unsigned int)); }
+  const unsigned int epoch = ++c->eval_epoch;
+  if (W > EV_MAXW) GLIO_CUDA_TRY(cudaMemcpyAsync(c->d_poses.p, c->h_poses.p, (size_t)W * 7 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+  eval_unary_run(c->d_items.p, c->n_items, W, c->d_poses.p, eval_params(c), jac_kind, want_jac, c->d_partials.p, c->h_out.p,
+                 c->d_kf_item_start.p, c->d_ticket.p, c->st, c->lc, c->h_flag.p, epoch, c->h_poses.p);
+  (void)cudaStreamQuery(c->st);            // pushes the launch to the device now (otherwise it may sit in the driver's queue until the next API call)
+  return epoch;
+}
+
+void eval_unary_wait(glio_ctx* c, unsigned int epoch) {
+  if (!epoch) return;
+  volatile unsigned int* flag = c->h_flag.p;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned long long spins = 0; *flag != epoch; ++spins) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((spins & 0x3ffull) == 0x3ffull) {
+      const cudaError_t q = cudaStreamQuery(c->st);
+      if (q != cudaSuccess && q != cudaErrorNotReady) GLIO_CUDA_TRY(q);
+      if (q == cudaSuccess && *flag != epoch) throw Error{GLIO_ERR_CUDA, "eval_unary: kernel finished without raising the completion flag"};
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 30.0) throw Error{GLIO_ERR_CUDA, "eval_unary: timed out waiting for the device"};
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+}
+
+// device evaluation of all active unary residuals -> c->h_out (W x 28: 21 upper-tri H, 6 g, 1 cost), synchronised
+void eval_unary_blocks(glio_ctx* c, int W, const double* poses_body, int jac_kind, bool want_jac) {
+  eval_unary_wait(c, eval_unary_launch(c, W, poses_body, jac_kind, want_jac));
 }
 
 }  // namespace
@@ -363,7 +400,7 @@ void glio_destroy(glio_ctx* c) {
   c->cell_count.release(); c->cell_pos.release(); c->scan_tmp.release(); c->d_segs.release(); c->d_dst.release(); c->d_counts.release();
   c->h_counts.release(); c->d_bad.release(); c->d_keep.release(); c->d_items.release(); c->d_kf_item_start.release();
   c->d_partials.release(); c->d_out.release(); c->d_poses.release(); c->d_r.release(); c->d_J.release(); c->h_out.release();
-  c->h_poses.release(); c->d_ticket.release(); c->w_knn_idx.release(); c->w_knn_sqd.release(); c->d_stats.release(); c->w_deferred.release();
+  c->h_poses.release(); c->h_flag.release(); c->d_ticket.release(); c->w_knn_idx.release(); c->w_knn_sqd.release(); c->d_stats.release(); c->w_deferred.release();
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
@@ -646,17 +683,21 @@ static int window_solve_impl(glio_ctx* c, int W, double* poses, double* speed_bi
         for (int i = 0; i < 7; ++i) pz[7 * k + i] = xa[(size_t)na * k + i];
         if (sb) for (int i = 0; i < 9; ++i) sz[9 * k + i] = xa[(size_t)na * k + 7 + i];
       }
-      eval_unary_blocks(c, W, pz.data(), 0, want_jac);
+      // the device evaluates the LiDAR residuals while the host evaluates its own factors
+      const unsigned int epoch = eval_unary_launch(c, W, pz.data(), 0, want_jac);
       double ct = 0;
-      for (int k = 0; k < W; ++k) ct += c->h_out.p[(size_t)k * GLIO_NACC + 27];
-      if (want_jac) {
-        std::fill(g, g + n, 0.0);
-        for (int k = 0; k < W; ++k) for (int p = 0; p < 6; ++p) g[nt * k + p] = c->h_out.p[(size_t)k * GLIO_NACC + 21 + p];
-      }
+      if (want_jac) std::fill(g, g + n, 0.0);
+      auto add_device = [&]() {
+        eval_unary_wait(c, epoch);
+        for (int k = 0; k < W; ++k) ct += c->h_out.p[(size_t)k * GLIO_NACC + 27];
+        if (want_jac) for (int k = 0; k < W; ++k) for (int p = 0; p < 6; ++p) g[nt * k + p] += c->h_out.p[(size_t)k * GLIO_NACC + 21 + p];
+      };
       if (host_band) {
         // host factors accumulate straight into the band matrix (no dense n x n scratch)
         if (want_jac) H->reset(n, hb_hint >= 5 ? hb_hint : n - 1);
-        if (host_band(user, W, pz.data(), sb ? sz.data() : nullptr, want_jac ? 1 : 0, want_jac ? H->a.data() : nullptr, want_jac ? H->hb : 0, g, &ct) != 0) return false;
+        const int hrc = host_band(user, W, pz.data(), sb ? sz.data() : nullptr, want_jac ? 1 : 0, want_jac ? H->a.data() : nullptr, want_jac ? H->hb : 0, g, &ct);
+        add_device();
+        if (hrc != 0) return false;
         if (want_jac) for (int k = 0; k < W; ++k) {
           const double* ob = c->h_out.p + (size_t)k * GLIO_NACC;
           int idx = 0;
@@ -665,10 +706,13 @@ static int window_solve_impl(glio_ctx* c, int W, double* poses, double* speed_bi
         *cost = ct;
         return std::isfinite(ct);
       }
+      int hrc = 0;
       if (host_factors) {
         if (want_jac) Hd.assign((size_t)n * n, 0.0);
-        if (host_factors(user, W, pz.data(), sb ? sz.data() : nullptr, want_jac ? 1 : 0, want_jac ? Hd.data() : nullptr, g, &ct) != 0) return false;
+        hrc = host_factors(user, W, pz.data(), sb ? sz.data() : nullptr, want_jac ? 1 : 0, want_jac ? Hd.data() : nullptr, g, &ct);
       }
+      add_device();
+      if (hrc != 0) return false;
       if (want_jac) {
         if (hb_fixed < 0) {
           // the block structure of the problem is fixed, so the band of J^T J is too (window: prior + IMU chain + unary

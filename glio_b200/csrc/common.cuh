@@ -194,10 +194,12 @@ struct EvalParams {
   double huber_delta;
 };
 constexpr int GLIO_NACC = 28;        // 21 upper-triangular H + 6 g + 1 cost
+constexpr int EV_MAXW = 64;          // poses are passed in the kernel parameters up to this many keyframes
 constexpr int GLIO_ITEM_MAX = 2048;  // residuals per evaluation work item
 void eval_unary_run(const EvalItem* d_items, int nitems, int W, const double* d_poses, const EvalParams& ep, int jac_kind,
                     bool want_jac, double* d_partials, double* d_out, const int* d_kf_item_start, unsigned int* d_ticket,
-                    cudaStream_t st, LaunchCounter& lc);
+                    cudaStream_t st, LaunchCounter& lc, unsigned int* done_flag = nullptr, unsigned int epoch = 0,
+                    const double* h_poses = nullptr);   // h_poses: host copy of the poses, passed by value when W <= EV_MAXW
 void eval_unary_residuals_run(const float4* cpw, const float4* nsd, int64_t n, const double* d_pose, const EvalParams& ep,
                               int jac_kind, double* d_r, double* d_J, cudaStream_t st, LaunchCounter& lc);
 

@@ -105,17 +105,21 @@ __device__ __forceinline__ void unary_accumulate(const float4 c4, const float4 n
 
 // One block per work item (a run of one keyframe's residuals, sized so the whole launch is about one wave of
 // 2 blocks/SM).  Loads are issued two iterations ahead of their use (4 x 16 B in flight per thread).
-template <bool WANT_JAC, int JAC_KIND>
+// poses of up to EV_MAXW keyframes travel in the kernel parameters (no host-to-device copy on the per-iteration path)
+struct PoseArgs { double p[EV_MAXW * 7]; };
+
+template <bool WANT_JAC, int JAC_KIND, bool POSE_ARGS>
 __global__ void __launch_bounds__(EV_T, 2) k_eval_unary(const EvalItem* __restrict__ items, int nitems, int W,
-                                                        const double* __restrict__ poses, EvalParams ep,
+                                                        const double* __restrict__ poses, const __grid_constant__ PoseArgs pa, EvalParams ep,
                                                         double* __restrict__ partials, double* __restrict__ out,
-                                                        const int* __restrict__ kf_item_start, unsigned int* __restrict__ ticket) {
+                                                        const int* __restrict__ kf_item_start, unsigned int* __restrict__ ticket,
+                                                        unsigned int* done_flag, unsigned int epoch) {
   __shared__ KfFrame F;
   __shared__ double red[EV_T / 32][NACC];
   __shared__ bool is_last;
   const EvalItem it = items[blockIdx.x];
   if (threadIdx.x == 0) {
-    const double* P = poses + 7 * it.kf;
+    const double* P = POSE_ARGS ? pa.p + 7 * it.kf : poses + 7 * it.kf;
     double qn[4] = {P[3], P[4], P[5], P[6]};
     double R[9]; quat_to_mat(qn, R);
     // q_lb^-1 = conj / |q|^2 (Eigen inverse()); rotation by it as the polynomial in its coefficients
@@ -186,21 +190,33 @@ __global__ void __launch_bounds__(EV_T, 2) k_eval_unary(const EvalItem* __restri
       for (int b = kf_item_start[kf]; b < kf_item_start[kf + 1]; ++b) v += partials[(size_t)b * NACC + k];
       out[o] = v;
     }
-    if (threadIdx.x == 0) *ticket = 0u;
+    // `out` may be host-mapped pinned memory: publish the W x NACC doubles system-wide, then raise the epoch flag the
+    // host spins on (no device-to-host copy, no stream synchronisation on the per-iteration path)
+    if (done_flag) { __threadfence_system(); __syncthreads(); }
+    if (threadIdx.x == 0) { *ticket = 0u; if (done_flag) *(volatile unsigned int*)done_flag = epoch; }
   }
 }
 
 void eval_unary_run(const EvalItem* d_items, int nitems, int W, const double* d_poses, const EvalParams& ep, int jac_kind,
                     bool want_jac, double* d_partials, double* d_out, const int* d_kf_item_start, unsigned int* d_ticket,
-                    cudaStream_t st, LaunchCounter& lc) {
+                    cudaStream_t st, LaunchCounter& lc, unsigned int* done_flag, unsigned int epoch, const double* h_poses) {
   if (nitems <= 0) {
     GLIO_CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)W * NACC * sizeof(double), st));
     return;
   }
   lc.begin(want_jac ? "k_eval_unary" : "k_eval_unary_cost", st);
-  if (!want_jac) k_eval_unary<false, 0><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, d_poses, ep, d_partials, d_out, d_kf_item_start, d_ticket);
-  else if (jac_kind == 0) k_eval_unary<true, 0><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, d_poses, ep, d_partials, d_out, d_kf_item_start, d_ticket);
-  else k_eval_unary<true, 1><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, d_poses, ep, d_partials, d_out, d_kf_item_start, d_ticket);
+  if (h_poses && W <= EV_MAXW) {
+    PoseArgs pa;
+    memcpy(pa.p, h_poses, (size_t)W * 7 * sizeof(double));
+    if (!want_jac) k_eval_unary<false, 0, true><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, nullptr, pa, ep, d_partials, d_out, d_kf_item_start, d_ticket, done_flag, epoch);
+    else if (jac_kind == 0) k_eval_unary<true, 0, true><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, nullptr, pa, ep, d_partials, d_out, d_kf_item_start, d_ticket, done_flag, epoch);
+    else k_eval_unary<true, 1, true><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, nullptr, pa, ep, d_partials, d_out, d_kf_item_start, d_ticket, done_flag, epoch);
+  } else {
+    static const PoseArgs none{};
+    if (!want_jac) k_eval_unary<false, 0, false><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, d_poses, none, ep, d_partials, d_out, d_kf_item_start, d_ticket, done_flag, epoch);
+    else if (jac_kind == 0) k_eval_unary<true, 0, false><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, d_poses, none, ep, d_partials, d_out, d_kf_item_start, d_ticket, done_flag, epoch);
+    else k_eval_unary<true, 1, false><<<nitems, EV_T, 0, st>>>(d_items, nitems, W, d_poses, none, ep, d_partials, d_out, d_kf_item_start, d_ticket, done_flag, epoch);
+  }
   lc.end(st);
   GLIO_CUDA_TRY(cudaGetLastError());
 }
