@@ -219,9 +219,39 @@ def run_glio(args, rank, world, local_rank):
     prof = ctx.lib_profile_read()
     n_fallback = ctx.knn_fallback_queries()
     ctx.lib_profile(False)
-    for _ in range(2):
-        one_step(hmap, hscans)
-    iters_e, ms_e, wall_e = timed_run(hmap, hscans, args.steps)
+    # (C) end to end through the C ABI with pinned HOST buffers.  Every step uploads its map (12 MB, in line) and the
+    #     20 scans of a window (24 MB); the scans of window i+1 are handed over right after the association of window i,
+    #     so their upload (copy stream) overlaps the solve of window i - the order a live system has (the next
+    #     keyframe's cloud arrives while the current window is optimised).  K steps = K map uploads + K scan uploads,
+    #     all inside the timed region; the prologue upload of the first window is outside it.
+    def timed_run_e2e(nsteps):
+        iters = 0
+        ctx.window_set_scans(hscans)
+        if dist is not None:
+            dist.barrier()
+        ctx.synchronize(); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(st)
+        for si in range(nsteps):
+            with torch.cuda.stream(st):
+                flush.fill_(1)
+            ctx.set_map(hmap)
+            ctx.window_associate(P["poses_init"])
+            ctx.window_set_scans(hscans)            # next window's scans: asynchronous, copy stream
+            r = ctx.window_solve(P["poses_init"], sb0, hf, opts, band=29)
+            iters += len(r["steps"])
+        ctx.synchronize()                           # both streams: the last upload is inside the timed region too
+        e1.record(st)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        if dist is not None:
+            dist.barrier()
+        return iters, ms, wall
+
+    timed_run_e2e(2)
+    iters_e, ms_e, wall_e = timed_run_e2e(args.steps)
     # wall-clock split of one resident step (every call ends synchronised, so these add up to the step)
     split = {}
     for _ in range(3):
@@ -292,7 +322,8 @@ def run_glio(args, rank, world, local_rank):
                                "K2 re-reads the 64 MB residual table every iteration as the real solve does",
                             host_wall_ms_per_step=1e3 * wall / args.steps, ms_per_step_with_kernel_events=ms_prof / args.steps, knn_deferred_queries_per_step=n_fallback / args.steps, wall_split=split,
                             solve_split_ms=dict(total=round(1e3 * s.total_seconds, 3), evaluation=round(1e3 * s.eval_seconds, 3), band_cholesky=round(1e3 * s.linear_solver_seconds, 3)), kernels=kern),
-                e2e=dict(value=e2e, unit="iterations/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=tmax_e / args.steps),
+                e2e=dict(value=e2e, unit="iterations/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=tmax_e / args.steps,
+                         how="pinned host buffers through the C ABI; per step: map upload (12 MB, in line) + the 20 scans of the next window (24 MB, copy stream, overlapping this window's solve) + per-iteration pose/result traffic; final poses read back"),
                 gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
     print(json.dumps(line))
     if dist is not None:

@@ -105,6 +105,9 @@ struct glio_ctx {
   DevBuf<int> d_kf_item_start;
   DevBuf<double> d_partials, d_out, d_poses, d_r, d_J;
   PinnedBuf<double> h_out, h_poses;
+  cudaStream_t st_copy = nullptr;       // window scans travel on their own stream so the upload of the next window can overlap a running solve
+  cudaEvent_t ev_scans = nullptr, ev_main = nullptr;
+  bool scans_pending = false;
   PinnedBuf<unsigned int> h_flag;      // completion epoch written by the last block of k_eval_unary
   unsigned int eval_epoch = 0;
   DevBuf<unsigned int> d_ticket;
@@ -182,6 +185,7 @@ AssocWork make_work(glio_ctx* c, int64_t Qt, bool pair) {
 void associate_slots(glio_ctx* c, const std::vector<int>& ids, const std::vector<std::array<double, 7>>& lidar_poses,
                      int64_t* n_match) {
   GLIO_REQUIRE(c->has_map, GLIO_ERR_STATE, "glio_set_map must be called before association");
+  if (c->scans_pending) { GLIO_CUDA_TRY(cudaStreamWaitEvent(c->st, c->ev_scans, 0)); c->scans_pending = false; }
   Trace tr(c->st, "associate");
   const int nseg = (int)ids.size();
   std::vector<SegDesc> segs(nseg);
@@ -378,6 +382,9 @@ int glio_create(int device, const glio_params* params, glio_ctx** out) {
     if (const char* e = getenv("GLIO_TILE_RINGS")) { const int v = atoi(e); if (v >= 1 && v < 64) c->tile_rings = v; }
     if (const char* e = getenv("GLIO_PTS_PER_CELL")) { const float v = (float)atof(e); if (v > 0.1f && v < 1000.f) c->pts_per_cell = v; }
     GLIO_CUDA_TRY(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    GLIO_CUDA_TRY(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+    GLIO_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_scans, cudaEventDisableTiming));
+    GLIO_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     { int sms = 148; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->eval_slots = 2 * sms; }
   });
   if (rc != GLIO_OK) { delete c; return rc; }
@@ -388,6 +395,7 @@ int glio_create(int device, const glio_params* params, glio_ctx** out) {
 void glio_destroy(glio_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->st_copy) cudaStreamSynchronize(c->st_copy);
   if (c->st) cudaStreamSynchronize(c->st);
   c->map.release(); c->map_stage.release();
   for (auto& f : c->frames) { f.second->scan.release(); f.second->grid.release(); }
@@ -401,6 +409,9 @@ void glio_destroy(glio_ctx* c) {
   c->h_counts.release(); c->d_bad.release(); c->d_keep.release(); c->d_items.release(); c->d_kf_item_start.release();
   c->d_partials.release(); c->d_out.release(); c->d_poses.release(); c->d_r.release(); c->d_J.release(); c->h_out.release();
   c->h_poses.release(); c->h_flag.release(); c->d_ticket.release(); c->w_knn_idx.release(); c->w_knn_sqd.release(); c->d_stats.release(); c->w_deferred.release();
+  if (c->ev_scans) cudaEventDestroy(c->ev_scans);
+  if (c->ev_main) cudaEventDestroy(c->ev_main);
+  if (c->st_copy) cudaStreamDestroy(c->st_copy);
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
@@ -409,7 +420,7 @@ const char* glio_last_error(const glio_ctx* c) { return c ? c->err.c_str() : glo
 
 int glio_synchronize(glio_ctx* c) {
   if (!c) return GLIO_ERR_ARG;
-  return guarded(c, [&] { GLIO_CUDA_TRY(cudaStreamSynchronize(c->st)); });
+  return guarded(c, [&] { GLIO_CUDA_TRY(cudaStreamSynchronize(c->st_copy)); GLIO_CUDA_TRY(cudaStreamSynchronize(c->st)); });
 }
 void* glio_stream(glio_ctx* c) { return c ? (void*)c->st : nullptr; }
 int64_t glio_launch_count(const glio_ctx* c) { return c ? c->lc.n : 0; }
@@ -527,12 +538,26 @@ int glio_window_set_scans(glio_ctx* c, int W, const float* const* scans, const i
   if (!c) return GLIO_ERR_ARG;
   return guarded(c, [&] {
     GLIO_REQUIRE(W > 0 && scans && Q, GLIO_ERR_ARG, "bad window arguments");
+    GLIO_REQUIRE(stride >= 3 && stride <= 64, GLIO_ERR_ARG, "stride_floats must be in [3,64]");
+    // Host scans are uploaded on the copy stream: the call returns at once and the next association waits for the
+    // event.  The matches of the previous association stay valid (they hold their own copies of the points), so the
+    // scans of the NEXT window can be handed over while the current window is still being solved.
+    if (mem != GLIO_DEVICE) {
+      GLIO_CUDA_TRY(cudaEventRecord(c->ev_main, c->st));
+      GLIO_CUDA_TRY(cudaStreamWaitEvent(c->st_copy, c->ev_main, 0));      // nothing queued on the main stream may still read the slot buffers
+    }
     for (int k = 0; k < W; ++k) {
       Slot& sl = c->slot(k);
-      sl.scan_ptr = stage_points(c, sl.scan, scans[k], Q[k], stride, mem);
-      sl.Q = Q[k]; sl.stride = stride; sl.n_match = 0; sl.n_sel = -1;
+      GLIO_REQUIRE(scans[k] != nullptr && Q[k] > 0, GLIO_ERR_ARG, "null or empty point array");
+      if (mem == GLIO_DEVICE) sl.scan_ptr = scans[k];
+      else {
+        sl.scan.reserve((size_t)Q[k] * stride);
+        GLIO_CUDA_TRY(cudaMemcpyAsync(sl.scan.p, scans[k], (size_t)Q[k] * stride * sizeof(float), cudaMemcpyHostToDevice, c->st_copy));
+        sl.scan_ptr = sl.scan.p;
+      }
+      sl.Q = Q[k]; sl.stride = stride;
     }
-    c->items_dirty = true;
+    if (mem != GLIO_DEVICE) { GLIO_CUDA_TRY(cudaEventRecord(c->ev_scans, c->st_copy)); c->scans_pending = true; }
   });
 }
 
