@@ -100,7 +100,11 @@ int glio_assoc_scan_to_map(glio_ctx* ctx, int slot, const float* scan_xyz, int64
 
 /* All W keyframes of the window in one launch (same results as W calls of glio_assoc_scan_to_map).
  * poses_body[W*7] are the keyframe (IMU-body) poses tmpTrans/tmpQuat; the lidar->map pose is formed on the
- * device-side host code exactly as Estimator.cpp:2216-2217 with params.q_lb/t_lb. */
+ * device-side host code exactly as Estimator.cpp:2216-2217 with params.q_lb/t_lb.
+ * glio_window_set_scans with GLIO_HOST buffers is ASYNCHRONOUS: the copies run on the context's copy stream and the next
+ * association waits for them, so the host buffers must stay valid until that association (or glio_synchronize) returns.
+ * It does not touch the matches of the previous association: the scans of the NEXT window may be handed over while the
+ * current window is still being solved (upload overlaps the solve). */
 int glio_window_set_scans(glio_ctx* ctx, int W, const float* const* scans, const int64_t* Q, int stride_floats, int mem);
 int glio_window_associate(glio_ctx* ctx, int W, const double* poses_body, int64_t* n_match /*W*/);
 
