@@ -133,7 +133,8 @@ class Context:
 
     KERNELS = ["k_knn_search", "k_knn_deferred", "k_knn_thread", "k_knn_box", "k_plane_fit", "k_plane_fit_pair", "k_eval_unary", "k_eval_unary_cost", "k_transform_hist", "k_order_scatter",
                "k_compact", "k_flags", "k_cell_hist", "k_cell_scatter", "k_load_bounds", "k_scan_block", "k_scan_add",
-               "k_eval_binary", "k_eval_binary_cost", "k_bin_assemble"]
+               "k_eval_binary", "k_eval_binary_cost", "k_bin_assemble",
+               "k_lm_transform", "k_vox_hist", "k_vox_scatter", "k_vox_sort", "k_vox_flags", "k_vox_centroid", "k_init_bounds"]
 
     def lib_profile(self, on):
         self._chk(self._lib.glio_profile_enable(self._h, C.c_int(1 if on else 0)))
@@ -164,6 +165,35 @@ class Context:
         self._chk(self._lib.glio_set_map(self._h, p, C.c_int64(n), C.c_int(stride), C.c_int(mem)))
 
     # ---- K1
+    # ---- local map maintenance on the device
+    def localmap_clear(self):
+        self._chk(self._lib.glio_localmap_clear(self._h))
+
+    def localmap_push(self, cloud_xyz, t, q, at_front=False):
+        keep, p, n, stride, mem = _points_arg(cloud_xyz)
+        t = np.ascontiguousarray(t, np.float64); q = np.ascontiguousarray(q, np.float64)
+        self._chk(self._lib.glio_localmap_push(self._h, C.c_int(1 if at_front else 0), p, C.c_int64(n), C.c_int(stride), C.c_int(mem), _ptr(t), _ptr(q)))
+
+    def localmap_pop_front(self):
+        self._chk(self._lib.glio_localmap_pop_front(self._h))
+
+    def localmap_size(self):
+        nf = C.c_int(0); npnt = C.c_int64(0)
+        self._chk(self._lib.glio_localmap_size(self._h, C.byref(nf), C.byref(npnt)))
+        return nf.value, int(npnt.value)
+
+    def localmap_build(self, leaf=0.4):
+        n = C.c_int64(0)
+        self._chk(self._lib.glio_localmap_build(self._h, C.c_float(leaf), C.byref(n)))
+        return int(n.value)
+
+    def get_map(self):
+        n = C.c_int64(0)
+        self._chk(self._lib.glio_get_map(self._h, C.c_int64(0), None, C.byref(n)))
+        out = np.empty((int(n.value), 3), np.float32)
+        self._chk(self._lib.glio_get_map(self._h, C.c_int64(len(out)), _ptr(out), C.byref(n)))
+        return out
+
     def assoc_scan_to_map(self, slot, scan_xyz, t, q):
         keep, p, n, stride, mem = _points_arg(scan_xyz)
         self._keep.append(keep); self._keep = self._keep[-64:]

@@ -3,6 +3,7 @@
 #include <array>
 #include <atomic>
 #include <chrono>
+#include <deque>
 #include <map>
 #include <memory>
 
@@ -105,6 +106,11 @@ struct glio_ctx {
   DevBuf<int> d_kf_item_start;
   DevBuf<double> d_partials, d_out, d_poses, d_r, d_J;
   PinnedBuf<double> h_out, h_poses;
+  // local map maintenance: world-frame keyframe clouds in deque order, concatenation, voxel filter work space
+  struct LmFrame { DevBuf<float4> pts; int64_t n = 0; };
+  std::deque<std::unique_ptr<LmFrame>> lm_frames;
+  std::vector<std::unique_ptr<LmFrame>> lm_spare;      // buffers of popped frames, reused by the next push (no cudaFree / cudaMalloc per keyframe)
+  DevBuf<float> lm_stage; DevBuf<float4> lm_cat; VoxelWork lm_vox; int64_t map_n = 0;
   cudaStream_t st_copy = nullptr;       // window scans travel on their own stream so the upload of the next window can overlap a running solve
   cudaEvent_t ev_scans = nullptr, ev_main = nullptr;
   bool scans_pending = false;
@@ -398,6 +404,9 @@ void glio_destroy(glio_ctx* c) {
   if (c->st_copy) cudaStreamSynchronize(c->st_copy);
   if (c->st) cudaStreamSynchronize(c->st);
   c->map.release(); c->map_stage.release();
+  for (auto& f : c->lm_frames) f->pts.release();
+  for (auto& f : c->lm_spare) f->pts.release();
+  c->lm_frames.clear(); c->lm_spare.clear(); c->lm_stage.release(); c->lm_cat.release(); c->lm_vox.release();
   for (auto& f : c->frames) { f.second->scan.release(); f.second->grid.release(); }
   for (auto& p : c->pairs) { p->m_cpw.release(); p->m_nc.release(); p->m_src.release(); p->s_cpw.release(); p->s_nc.release(); }
   c->d_bin_items.release(); c->d_pair_item_start.release(); c->d_kf_inc_start.release(); c->d_inc.release(); c->d_bin_partials.release();
@@ -515,7 +524,91 @@ int glio_set_map(glio_ctx* c, const float* xyz, int64_t M, int stride, int mem) 
     GLIO_REQUIRE(M >= 5, GLIO_ERR_ARG, "map needs at least 5 points");
     const float* d = stage_points(c, c->map_stage, xyz, M, stride, mem);
     grid_build(c->map, d, stride, M, nullptr, nullptr, c->prm.cell_size, c->pts_per_cell, c->st, c->lc);
+    c->has_map = true; c->map_n = M;
+  });
+}
+
+// ---- local map maintenance on the device (Estimator.cpp:3529-3631 buildLocalMapWithLandMark, :3615-3618 downSampleCloud) ----
+int glio_localmap_clear(glio_ctx* c) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    for (auto& f : c->lm_frames) f->pts.release();
+    c->lm_frames.clear();
+  });
+}
+
+int glio_localmap_push(glio_ctx* c, int at_front, const float* cloud_xyz, int64_t n, int stride, int mem, const double t[3], const double q[4]) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(t && q, GLIO_ERR_ARG, "null pose");
+    const float* d = stage_points(c, c->lm_stage, cloud_xyz, n, stride, mem);
+    std::unique_ptr<glio_ctx::LmFrame> f;
+    if (!c->lm_spare.empty()) { f = std::move(c->lm_spare.back()); c->lm_spare.pop_back(); }
+    else f = std::make_unique<glio_ctx::LmFrame>();
+    f->pts.reserve((size_t)n); f->n = n;
+    localmap_transform(d, stride, n, t, q, f->pts.p, c->st, c->lc);        // transformCloud: float(q*double(p)+t)
+    if (mem != GLIO_DEVICE) GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));    // the staging buffer is reused by the next push
+    if (at_front) c->lm_frames.push_front(std::move(f)); else c->lm_frames.push_back(std::move(f));
+  });
+}
+
+int glio_localmap_pop_front(glio_ctx* c) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(!c->lm_frames.empty(), GLIO_ERR_STATE, "local map holds no keyframe cloud");
+    // the stream is ordered: anything still reading the popped buffer was enqueued before whatever reuses it
+    c->lm_spare.push_back(std::move(c->lm_frames.front()));
+    c->lm_frames.pop_front();
+  });
+}
+
+int glio_localmap_size(glio_ctx* c, int* n_frames, int64_t* n_points) {
+  if (!c) return GLIO_ERR_ARG;
+  int64_t np = 0;
+  for (auto& f : c->lm_frames) np += f->n;
+  if (n_frames) *n_frames = (int)c->lm_frames.size();
+  if (n_points) *n_points = np;
+  return GLIO_OK;
+}
+
+int glio_localmap_build(glio_ctx* c, float leaf, int64_t* n_map) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    int64_t N = 0;
+    for (auto& f : c->lm_frames) N += f->n;
+    GLIO_REQUIRE(N >= 5, GLIO_ERR_STATE, "local map needs at least 5 points");
+    c->lm_cat.reserve((size_t)N);
+    int64_t o = 0;
+    for (auto& f : c->lm_frames) {                                          // *surf_local_map += *recent_surf_keyframes[i]
+      GLIO_CUDA_TRY(cudaMemcpyAsync(c->lm_cat.p + o, f->pts.p, (size_t)f->n * sizeof(float4), cudaMemcpyDeviceToDevice, c->st));
+      o += f->n;
+    }
+    const int64_t m = leaf > 0.f ? voxel_filter_run(c->lm_vox, c->lm_cat.p, N, leaf, c->st, c->lc) : -1;   // ds_filter_surf_map.filter
+    if (m >= 0) {
+      GLIO_REQUIRE(m >= 5, GLIO_ERR_STATE, "down-sampled local map has fewer than 5 points");
+      grid_build(c->map, c->lm_vox.out_xyz.p, 3, m, nullptr, nullptr, c->prm.cell_size, c->pts_per_cell, c->st, c->lc);   // kd_tree_surf_local_map->setInputCloud
+      c->map_n = m;
+    } else {                                                                // leaf <= 0, or PCL's pass-through when the voxel grid would overflow
+      grid_build(c->map, reinterpret_cast<const float*>(c->lm_cat.p), 4, N, nullptr, nullptr, c->prm.cell_size, c->pts_per_cell, c->st, c->lc);
+      c->map_n = N;
+    }
     c->has_map = true;
+    if (n_map) *n_map = c->map_n;
+  });
+}
+
+int glio_get_map(glio_ctx* c, int64_t capacity, float* xyz, int64_t* n_out) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(c->has_map, GLIO_ERR_STATE, "no map set");
+    const int64_t n = std::min<int64_t>(capacity, c->map_n);
+    if (n_out) *n_out = c->map_n;
+    if (n <= 0 || !xyz) return;
+    std::vector<float> h((size_t)n * 4);
+    GLIO_CUDA_TRY(cudaMemcpyAsync(h.data(), c->map.tmp4.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->st));
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    for (int64_t i = 0; i < n; ++i) { xyz[3 * i] = h[4 * i]; xyz[3 * i + 1] = h[4 * i + 1]; xyz[3 * i + 2] = h[4 * i + 2]; }
   });
 }
 

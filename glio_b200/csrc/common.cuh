@@ -174,6 +174,17 @@ void grid_build(GridBuild& gb, const float* d_xyz, int stride, int64_t n, const 
                 float cell_size_hint, float pts_per_cell, cudaStream_t st, LaunchCounter& lc);
 void exclusive_scan_i32(const int* in, int* out, int64_t n, DevBuf<int>& tmp, cudaStream_t st, LaunchCounter& lc);
 
+// ---- local map maintenance (grid.cu): world-frame keyframe clouds -> pcl::VoxelGrid-style down-sampling
+struct VoxelWork {
+  DevBuf<float4> tmp4;
+  DevBuf<int> bounds, count, start, opos, order, sorted, scan_tmp, out_vox;
+  DevBuf<float> out_xyz;      // filtered points, 3 floats each, ascending voxel index
+  void release() { tmp4.release(); bounds.release(); count.release(); start.release(); opos.release(); order.release(); sorted.release(); scan_tmp.release(); out_vox.release(); out_xyz.release(); }
+};
+void localmap_transform(const float* d_xyz, int stride, int64_t n, const double* t, const double* q, float4* d_out, cudaStream_t st, LaunchCounter& lc);
+// returns the number of filtered points (in w.out_xyz / w.out_vox), or -1 when PCL would pass the input through unchanged
+int64_t voxel_filter_run(VoxelWork& w, const float4* d_in, int64_t n, float leaf, cudaStream_t st, LaunchCounter& lc);
+
 // ---- K1 / K1b (assoc.cu)
 void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const AssocWork& w, const AssocGates& gates,
                const float* oth_local, int oth_stride, DevBuf<int>& cell_count, DevBuf<int>& cell_pos,

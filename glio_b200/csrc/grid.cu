@@ -213,4 +213,186 @@ void grid_build(GridBuild& gb, const float* d_xyz, int stride, int64_t n, const 
   g.pts = gb.pts.p;
 }
 
+// =====================================================================================================================
+// Local map maintenance on the device: keyframe clouds moved to the world frame when they are pushed
+// (transformCloud, Estimator.cpp:1517-1545), concatenated, then pcl::VoxelGrid down-sampling as GLIO configures it
+// (ds_filter_surf_map, leaf 0.4 m, Estimator.cpp:854, 3617-3618).  The voxel filter is a counting sort by PCL's voxel
+// index (float min/max, min_b = floor(min*inv_leaf), idx = ijk0 + ijk1*div0 + ijk2*div0*div1) followed by a per-voxel float
+// sum in INPUT order and a float division by the count; output in ascending voxel index (PCL's output order).
+// PCL sums the points of a voxel in whatever order std::sort leaves them; summing in input order is the deterministic
+// member of that family (the stable order).
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) k_lm_transform(const float* __restrict__ xyz, int stride, int64_t n, PoseD pose, float4* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float p[3] = {xyz[i * stride], xyz[i * stride + 1], xyz[i * stride + 2]};
+    transform_point_f(pose, p, p);
+    out[i] = make_float4(p[0], p[1], p[2], 0.f);
+  }
+}
+
+void localmap_transform(const float* d_xyz, int stride, int64_t n, const double* t, const double* q, float4* d_out, cudaStream_t st, LaunchCounter& lc) {
+  PoseD pose;
+  for (int k = 0; k < 3; ++k) pose.t[k] = t[k];
+  for (int k = 0; k < 4; ++k) pose.q[k] = q[k];
+  const int nb = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  lc.begin("k_lm_transform", st); k_lm_transform<<<nb, 256, 0, st>>>(d_xyz, stride, n, pose, d_out); lc.end(st);
+  GLIO_CUDA_TRY(cudaGetLastError());
+}
+
+struct VoxelDesc { float inv; int min_b[3]; int div0, div01; };
+__device__ __forceinline__ int voxel_of(const VoxelDesc& v, float x, float y, float z) {
+  const int i0 = (int)__fsub_rn(floorf(__fmul_rn(x, v.inv)), (float)v.min_b[0]);
+  const int i1 = (int)__fsub_rn(floorf(__fmul_rn(y, v.inv)), (float)v.min_b[1]);
+  const int i2 = (int)__fsub_rn(floorf(__fmul_rn(z, v.inv)), (float)v.min_b[2]);
+  return i0 + i1 * v.div0 + i2 * v.div01;
+}
+__global__ void __launch_bounds__(256) k_vox_hist(const float4* __restrict__ pts, int64_t n, VoxelDesc v, int* __restrict__ count) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    atomicAdd(&count[voxel_of(v, p.x, p.y, p.z)], 1);
+  }
+}
+__global__ void __launch_bounds__(256) k_vox_scatter(const float4* __restrict__ pts, int64_t n, VoxelDesc v, const int* __restrict__ start,
+                                                     int* __restrict__ fill, int* __restrict__ order) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    const int c = voxel_of(v, p.x, p.y, p.z);
+    order[start[c] + atomicAdd(&fill[c], 1)] = (int)i;
+  }
+}
+// Order the point indices of every voxel ascending (= input order): the atomic scatter leaves them in arrival order.
+// One warp per voxel: bitonic sort of 32*K keys held K per lane (shuffles for partner distances < 32, register swaps
+// above); voxels with more than 256 points fall back to counting ranks.
+template <int K>
+__device__ __forceinline__ void warp_bitonic_sort(int (&v)[K], int lane) {
+  constexpr int N = 32 * K;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int jr = j >> 5;
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+          const int pr = r ^ jr;
+          if (pr > r) {
+            const bool asc = (((r << 5) + lane) & k) == 0;
+            const int a = v[r], b = v[pr];
+            const bool sw = asc ? (a > b) : (a < b);
+            v[r] = sw ? b : a; v[pr] = sw ? a : b;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+          const bool asc = (((r << 5) + lane) & k) == 0;
+          const int o = __shfl_xor_sync(0xffffffffu, v[r], j);
+          const bool lower = (lane & j) == 0;
+          v[r] = (lower == asc) ? min(v[r], o) : max(v[r], o);
+        }
+      }
+    }
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void sort_segment(const int* __restrict__ order, int* __restrict__ sorted, int s, int n, int lane) {
+  int v[K];
+#pragma unroll
+  for (int r = 0; r < K; ++r) { const int i = (r << 5) + lane; v[r] = i < n ? order[s + i] : 0x7fffffff; }
+  warp_bitonic_sort<K>(v, lane);
+#pragma unroll
+  for (int r = 0; r < K; ++r) { const int i = (r << 5) + lane; if (i < n) sorted[s + i] = v[r]; }
+}
+
+__global__ void __launch_bounds__(256) k_vox_sort(const int* __restrict__ start, int64_t nvox, const int* __restrict__ order, int* __restrict__ sorted) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t c0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; c0 < nvox; c0 += nwarps * 32) {
+    // the 32 lanes look at 32 consecutive voxels, then the warp serves the non-empty ones in turn
+    const int64_t c = c0 + lane;
+    int s = 0, n = 0;
+    if (c < nvox) { s = start[c]; n = start[c + 1] - s; }
+    unsigned m = __ballot_sync(0xffffffffu, n > 0);
+    while (m) {
+      const int l = __ffs(m) - 1; m &= m - 1;
+      const int ss = __shfl_sync(0xffffffffu, s, l), nn = __shfl_sync(0xffffffffu, n, l);
+      if (nn == 1) { if (lane == 0) sorted[ss] = order[ss]; }
+      else if (nn <= 32) sort_segment<1>(order, sorted, ss, nn, lane);
+      else if (nn <= 64) sort_segment<2>(order, sorted, ss, nn, lane);
+      else if (nn <= 128) sort_segment<4>(order, sorted, ss, nn, lane);
+      else if (nn <= 256) sort_segment<8>(order, sorted, ss, nn, lane);
+      else {
+        for (int i = lane; i < nn; i += 32) {
+          const int key = order[ss + i];
+          int r = 0;
+          for (int k = 0; k < nn; ++k) r += order[ss + k] < key ? 1 : 0;
+          sorted[ss + r] = key;
+        }
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_vox_flags(const int* __restrict__ start, int64_t nvox, int* __restrict__ flags) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nvox) flags[c] = start[c + 1] > start[c] ? 1 : 0;
+  if (c == nvox) flags[c] = 0;
+}
+__global__ void __launch_bounds__(256) k_vox_centroid(const float4* __restrict__ pts, const int* __restrict__ start, const int* __restrict__ sorted,
+                                                      const int* __restrict__ opos, int64_t nvox, float* __restrict__ out_xyz, int* __restrict__ out_vox) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nvox) return;
+  const int s = start[c], e = start[c + 1];
+  if (e <= s) return;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int k = s; k < e; ++k) { const float4 p = pts[sorted[k]]; sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); }
+  const float cnt = (float)(e - s);
+  const int o = opos[c];
+  out_xyz[3 * (size_t)o] = __fdiv_rn(sx, cnt); out_xyz[3 * (size_t)o + 1] = __fdiv_rn(sy, cnt); out_xyz[3 * (size_t)o + 2] = __fdiv_rn(sz, cnt);
+  if (out_vox) out_vox[o] = (int)c;
+}
+
+int64_t voxel_filter_run(VoxelWork& w, const float4* d_in, int64_t n, float leaf, cudaStream_t st, LaunchCounter& lc) {
+  GLIO_REQUIRE(n > 0 && n < ((int64_t)1 << 31), GLIO_ERR_ARG, "voxel_filter: bad point count");
+  GLIO_REQUIRE(leaf > 0.f, GLIO_ERR_ARG, "voxel_filter: leaf size must be positive");
+  w.tmp4.reserve((size_t)n); w.bounds.reserve(8);
+  lc.begin("k_init_bounds", st); k_init_bounds<<<1, 32, 0, st>>>(w.bounds.p); lc.end(st);
+  const int nb = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  PoseD none{};
+  lc.begin("k_load_bounds", st); k_load_bounds<<<nb, 256, 0, st>>>(reinterpret_cast<const float*>(d_in), 4, n, none, 0, w.tmp4.p, w.bounds.p); lc.end(st);
+  int hb[6];
+  GLIO_CUDA_TRY(cudaMemcpyAsync(hb, w.bounds.p, sizeof(hb), cudaMemcpyDeviceToHost, st));
+  GLIO_CUDA_TRY(cudaStreamSynchronize(st));
+  float mn[3], mx[3];
+  for (int d = 0; d < 3; ++d) { mn[d] = ordered_to_float_h(hb[d]); mx[d] = ordered_to_float_h(hb[3 + d]); }
+  for (int d = 0; d < 3; ++d) GLIO_REQUIRE(std::isfinite(mn[d]) && std::isfinite(mx[d]), GLIO_ERR_ARG, "voxel_filter: non-finite point coordinates");
+  const float inv = 1.0f / leaf;                               // setLeafSize: Array4f::Ones() / leaf
+  const int64_t dx = (int64_t)((mx[0] - mn[0]) * inv) + 1, dy = (int64_t)((mx[1] - mn[1]) * inv) + 1, dz = (int64_t)((mx[2] - mn[2]) * inv) + 1;
+  if (dx * dy * dz > (int64_t)0x7fffffff) return -1;           // PCL: "leaf size too small", input passed through
+  VoxelDesc v; v.inv = inv;
+  int div[3];
+  for (int d = 0; d < 3; ++d) { v.min_b[d] = (int)std::floor(mn[d] * inv); div[d] = (int)std::floor(mx[d] * inv) - v.min_b[d] + 1; }
+  v.div0 = div[0]; v.div01 = div[0] * div[1];
+  const int64_t nvox = (int64_t)div[0] * div[1] * div[2];
+  GLIO_REQUIRE(nvox <= (int64_t)256 * 1024 * 1024, GLIO_ERR_ARG, "voxel_filter: more than 2^28 voxels in the bounding box (dense voxel table)");
+  w.count.reserve((size_t)nvox + 2); w.start.reserve((size_t)nvox + 2); w.opos.reserve((size_t)nvox + 2);
+  w.order.reserve((size_t)n); w.sorted.reserve((size_t)n); w.out_xyz.reserve((size_t)n * 3); w.out_vox.reserve((size_t)n);
+  GLIO_CUDA_TRY(cudaMemsetAsync(w.count.p, 0, (size_t)(nvox + 1) * sizeof(int), st));
+  lc.begin("k_vox_hist", st); k_vox_hist<<<nb, 256, 0, st>>>(w.tmp4.p, n, v, w.count.p); lc.end(st);
+  exclusive_scan_i32(w.count.p, w.start.p, nvox + 1, w.scan_tmp, st, lc);
+  GLIO_CUDA_TRY(cudaMemsetAsync(w.count.p, 0, (size_t)(nvox + 1) * sizeof(int), st));
+  lc.begin("k_vox_scatter", st); k_vox_scatter<<<nb, 256, 0, st>>>(w.tmp4.p, n, v, w.start.p, w.count.p, w.order.p); lc.end(st);
+  lc.begin("k_vox_sort", st); k_vox_sort<<<148 * 8, 256, 0, st>>>(w.start.p, nvox, w.order.p, w.sorted.p); lc.end(st);
+  const unsigned nbv = (unsigned)((nvox + 1 + 255) / 256);
+  lc.begin("k_vox_flags", st); k_vox_flags<<<nbv, 256, 0, st>>>(w.start.p, nvox, w.count.p); lc.end(st);
+  exclusive_scan_i32(w.count.p, w.opos.p, nvox + 1, w.scan_tmp, st, lc);
+  lc.begin("k_vox_centroid", st); k_vox_centroid<<<nbv, 256, 0, st>>>(w.tmp4.p, w.start.p, w.sorted.p, w.opos.p, nvox, w.out_xyz.p, w.out_vox.p); lc.end(st);
+  int m = 0;
+  GLIO_CUDA_TRY(cudaMemcpyAsync(&m, w.opos.p + nvox, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GLIO_CUDA_TRY(cudaStreamSynchronize(st));
+  GLIO_CUDA_TRY(cudaGetLastError());
+  return (int64_t)m;
+}
+
+
 }  // namespace glio

@@ -90,6 +90,28 @@ void glio_lidar_pose(const glio_params* prm, const double pose_body[7], double t
  * Replaces kd_tree_surf_local_map->setInputCloud(surf_local_map_ds)  (Estimator.cpp:2056). */
 int glio_set_map(glio_ctx* ctx, const float* xyz, int64_t M, int stride_floats, int mem);
 
+/* ---- Local map maintenance on the device.
+ * Replaces Estimator::buildLocalMapWithLandMark (Estimator.cpp:3529-3610: the deque `recent_surf_keyframes` of
+ * world-frame keyframe clouds and their concatenation `surf_local_map`) and the map half of downSampleCloud
+ * (:3615-3618: ds_filter_surf_map, pcl::VoxelGrid leaf 0.4 m set at :854) followed by
+ * kd_tree_surf_local_map->setInputCloud (:2056).  The keyframe clouds stay resident on the GPU; only a new keyframe's
+ * cloud crosses PCIe.
+ *   glio_localmap_push       recent_surf_keyframes.push_front / push_back(transformCloud(cloud, {t, q}))   (:3574, :3600)
+ *                            with t = q_po*t_bl + t_po, q = q_po*q_bl formed by the caller as at :3563-3564
+ *   glio_localmap_pop_front  recent_surf_keyframes.pop_front()                                               (:3580)
+ *   glio_localmap_clear      recent_surf_keyframes.clear()                                                   (:3549)
+ *   glio_localmap_build      concatenate (:3605-3608), VoxelGrid(leaf) (:3617-3618), make it the searchable map; leaf <= 0
+ *                            skips the filter.  PCL sums the points of a voxel in the order std::sort leaves them; this
+ *                            sums them in input order (the deterministic member of that family).
+ *   glio_get_map             the points of the current map in their original order (filtered map: ascending voxel index). */
+int glio_localmap_clear(glio_ctx* ctx);
+int glio_localmap_push(glio_ctx* ctx, int at_front, const float* cloud_xyz, int64_t n, int stride_floats, int mem,
+                       const double t[3], const double q[4]);
+int glio_localmap_pop_front(glio_ctx* ctx);
+int glio_localmap_size(glio_ctx* ctx, int* n_frames, int64_t* n_points);
+int glio_localmap_build(glio_ctx* ctx, float leaf, int64_t* n_map);
+int glio_get_map(glio_ctx* ctx, int64_t capacity, float* xyz, int64_t* n_map);
+
 /* ---- K1: scan-to-map surf association for ONE keyframe slot.
  * Replaces Estimator::findCorrespondingSurfFeatures(idx, q, t)  (Estimator.cpp:3633-3708):
  * q,t is the lidar->map pose (Q2,T2 of Estimator.cpp:2216-2217).  The scan stays resident in the slot.

@@ -314,6 +314,44 @@ void go_transform_points(const float* in_xyz, int64_t n, const double t[3], cons
   for (int64_t i = 0; i < n; ++i) transform_pt<float>(q, t, in_xyz + 3 * i, out_xyz + 3 * i);
 }
 
+int64_t go_voxel_filter(const float* xyz, int64_t n, float leaf, int order_mode, float* out_xyz, int32_t* out_idx) {
+  if (n <= 0) return 0;
+  // setLeafSize: inverse_leaf_size_ = Eigen::Array4f::Ones() / leaf_size_.array()  (float division)
+  const float inv = 1.0f / leaf;
+  // getMinMax3D: float min / max over the points
+  float mn[3] = {xyz[0], xyz[1], xyz[2]}, mx[3] = {xyz[0], xyz[1], xyz[2]};
+  for (int64_t i = 1; i < n; ++i) for (int d = 0; d < 3; ++d) { mn[d] = std::min(mn[d], xyz[3 * i + d]); mx[d] = std::max(mx[d], xyz[3 * i + d]); }
+  // leaf-size sanity check of applyFilter
+  const int64_t dx = (int64_t)((mx[0] - mn[0]) * inv) + 1, dy = (int64_t)((mx[1] - mn[1]) * inv) + 1, dz = (int64_t)((mx[2] - mn[2]) * inv) + 1;
+  if (dx * dy * dz > (int64_t)std::numeric_limits<int32_t>::max()) return -1;
+  int min_b[3], max_b[3], div_b[3];
+  for (int d = 0; d < 3; ++d) { min_b[d] = (int)std::floor(mn[d] * inv); max_b[d] = (int)std::floor(mx[d] * inv); div_b[d] = max_b[d] - min_b[d] + 1; }
+  const int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+  struct Cpi { unsigned int idx; unsigned int cloud_point_index; bool operator<(const Cpi& o) const { return idx < o.idx; } };
+  std::vector<Cpi> iv; iv.reserve((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    const int ijk0 = (int)(std::floor(xyz[3 * i] * inv) - (float)min_b[0]);
+    const int ijk1 = (int)(std::floor(xyz[3 * i + 1] * inv) - (float)min_b[1]);
+    const int ijk2 = (int)(std::floor(xyz[3 * i + 2] * inv) - (float)min_b[2]);
+    iv.push_back(Cpi{(unsigned int)(ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2]), (unsigned int)i});
+  }
+  if (order_mode == 0) std::sort(iv.begin(), iv.end());
+  else std::stable_sort(iv.begin(), iv.end());
+  int64_t m = 0;
+  for (size_t a = 0; a < iv.size();) {
+    size_t b = a + 1;
+    while (b < iv.size() && iv[b].idx == iv[a].idx) ++b;
+    // CentroidPoint<PointXYZI>: AccumulatorXYZ sums Eigen::Vector3f, get() divides by the count
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (size_t k = a; k < b; ++k) { const float* q = xyz + 3 * (size_t)iv[k].cloud_point_index; sx += q[0]; sy += q[1]; sz += q[2]; }
+    const float cnt = (float)(b - a);
+    out_xyz[3 * m] = sx / cnt; out_xyz[3 * m + 1] = sy / cnt; out_xyz[3 * m + 2] = sz / cnt;
+    if (out_idx) out_idx[m] = (int32_t)iv[a].idx;
+    ++m; a = b;
+  }
+  return m;
+}
+
 void go_knn5_brute(const float* map_xyz, int64_t M, const float* qry_xyz, int64_t Q, int32_t* idx5, float* sqd5, uint8_t* tie) {
 #pragma omp parallel for schedule(dynamic, 64)
   for (int64_t i = 0; i < Q; ++i) {

@@ -48,6 +48,18 @@ void go_transform_points(const float* in_xyz, int64_t n, const double t[3], cons
 
 /* exact 5-NN, brute force, FLANN L2_Simple<float> accumulation order, ties broken by index.
  * tie[i] = 1 if the 5th/6th (or any adjacent pair among the first 6) distances are equal. */
+/* Local map down-sampling: pcl::VoxelGrid<PointXYZI>::applyFilter as GLIO uses it (ds_filter_surf_map, leaf 0.4 m,
+ * Estimator.cpp:854, :3617-3618; downsample_all_data = true, min_points_per_voxel = 0), xyz only.
+ * PCL is a dependency that is NOT in /root/reference (ROS's libpcl 1.8/1.10): this restates its published algorithm
+ * (filters/include/pcl/filters/impl/voxel_grid.hpp applyFilter: float min/max, min_b = floor(min * inv_leaf),
+ * idx = ijk0 + ijk1*div0 + ijk2*div0*div1 with ijk = int(floor(p*inv_leaf) - float(min_b)), std::sort by idx, per-voxel
+ * float sums divided by the float count, output in ascending voxel index).  order_mode 0: literal std::sort (the order of
+ * points inside a voxel - hence the last bits of the float sums - is whatever introsort leaves); order_mode 1: stable
+ * (points of a voxel summed in input order), the variant the CUDA path reproduces bit-for-bit.
+ * Returns the number of output points (<= n); out_xyz needs room for n points; out_idx (optional) receives each output
+ * point's voxel index.  If the grid would overflow int32 PCL copies the input unchanged: returns -1. */
+int64_t go_voxel_filter(const float* xyz, int64_t n, float leaf, int order_mode, float* out_xyz, int32_t* out_idx);
+
 void go_knn5_brute(const float* map_xyz, int64_t M, const float* qry_xyz, int64_t Q,
                    int32_t* idx5, float* sqd5, uint8_t* tie);
 

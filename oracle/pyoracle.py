@@ -72,6 +72,17 @@ def transform_points(xyz, t, q):
     return out
 
 
+def voxel_filter(xyz, leaf=0.4, stable=True):
+    """pcl::VoxelGrid restatement (see glio_oracle.h).  Returns (points, voxel_idx) or None when PCL would pass the input through."""
+    x = _f32(xyz).reshape(-1, 3); n = len(x)
+    out = np.empty((n, 3), np.float32); idx = np.empty(n, np.int32)
+    lib().go_voxel_filter.restype = C.c_int64
+    m = lib().go_voxel_filter(_p(x), C.c_int64(n), C.c_float(leaf), C.c_int(1 if stable else 0), _p(out), _p(idx))
+    if m < 0:
+        return None
+    return out[:m].copy(), idx[:m].copy()
+
+
 def knn5_brute(map_xyz, qry_xyz):
     m = _f32(map_xyz).reshape(-1, 3); q = _f32(qry_xyz).reshape(-1, 3)
     idx = np.empty((len(q), 5), np.int32); sqd = np.empty((len(q), 5), np.float32)
