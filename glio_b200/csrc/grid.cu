@@ -125,12 +125,20 @@ __global__ void __launch_bounds__(256) k_load_bounds(const float* __restrict__ x
       mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
     }
   }
+  // one set of global atomics per block (8 warps -> shared memory -> thread 0), not per warp
+  __shared__ float smn[8][3], smx[8][3];
+  const int wid = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      atomicMin(&bounds[d], float_to_ordered(mn[d]));
-      atomicMax(&bounds[3 + d], float_to_ordered(mx[d]));
-    }
+    for (int d = 0; d < 3; ++d) { smn[wid][d] = mn[d]; smx[wid][d] = mx[d]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int d = threadIdx.x;
+    float a = smn[0][d], b = smx[0][d];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a = fminf(a, smn[w][d]); b = fmaxf(b, smx[w][d]); }
+    atomicMin(&bounds[d], float_to_ordered(a));
+    atomicMax(&bounds[3 + d], float_to_ordered(b));
   }
 }
 
