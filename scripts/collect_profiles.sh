@@ -8,5 +8,5 @@ mkdir -p gpurun_out
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_line.json 2> gpurun_out/bench_err.log
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference_line.json 2>> gpurun_out/bench_err.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/b_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_knn_box|k_plane_fit|k_eval_unary" -s 9 -c 4 -o gpurun_out/prof_top python scripts/probe.py > gpurun_out/ncu_top.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_knn_box|k_plane_fit|k_eval_unary" -c 16 -f -o gpurun_out/prof_top python scripts/probe.py > gpurun_out/ncu_top.log 2>&1
 ls -la gpurun_out

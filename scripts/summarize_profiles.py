@@ -46,11 +46,34 @@ if os.path.exists(rep):
     rows = list(csv.reader(out.splitlines())); h, units = rows[0], rows[1]
     with open(os.path.join(P, rnd + "_ncu_top_kernels.txt"), "w") as f:
         f.write("# round %s — ncu --set full --clock-control none --import-source on (one capture per kernel, B200, cfg 2 sizes: M=1M map, 2M queries, 2.0M residuals)\n" % rnd[1:])
-        for r in rows[2:]:
+        last = {}
+        for r in rows[2:]: last[r[h.index("Kernel Name")]] = r            # several launches are captured: keep the last (warm) one of each kernel
+        for r in last.values():
             f.write("\n## %s\n" % r[h.index("Kernel Name")][:90])
             for w in WANT:
                 if w in h: f.write("  %-100s %16s %s\n" % (w, r[h.index(w)], units[h.index(w)]))
-    print("wrote ncu summary (%d kernels)" % (len(rows) - 2))
+    print("wrote ncu summary (%d kernels of %d captured launches)" % (len(last), len(rows) - 2))
+
+# ---- DRAM traffic per launch of the roofline kernels (bench.py reads profiles/ncu_traffic.json into roofline.traffic) ----
+def _traffic(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    if len(rows) < 3: return {}
+    h, u = rows[0], rows[1]; res = {}
+    for r in rows[2:]:
+        name = re.sub(r"^(void )?(glio::)?", "", r[h.index("Kernel Name")]); name = re.sub(r"[<(].*$", "", name)
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(r[h.index(m)].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u[h.index(m)], 1)
+        res.setdefault(name, []).append(tot)
+    return {k: sum(v) / len(v) for k, v in res.items()}
+tr = {}
+for rep in ("prof_top.ncu-rep",):
+    if os.path.exists(os.path.join(G, rep)): tr.update(_traffic(os.path.join(G, rep)))
+if tr:
+    tr = {k: round(v) for k, v in tr.items()}
+    tr["_source"] = "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum per launch, cfg 2 sizes (gpurun_out/prof_top.ncu-rep of round %s, mean over the captured launches)" % rnd[1:]
+    json.dump(tr, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1); print("wrote ncu_traffic.json", tr)
 
 for name in ("bench_line.json", "bench_reference_line.json"):
     s = os.path.join(G, name)
