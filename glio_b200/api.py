@@ -493,6 +493,14 @@ def _eval_edge(self, poses_body, want_jac=True):
 
 Context.set_edges = _set_edges
 Context.eval_edge = _eval_edge
+def _batch_set_pair_matches(self, cur, oth, cp, normal_cent, weight):
+    """Upload the matches of pair (cur, oth) instead of associating them (score = batch_score * weight)."""
+    cp = np.ascontiguousarray(cp, np.float32).reshape(-1, 3); nc = np.ascontiguousarray(normal_cent, np.float64).reshape(-1, 6)
+    w = np.ascontiguousarray(weight, np.float32)
+    self._chk(self._lib.glio_batch_set_pair_matches(self._h, C.c_int(cur), C.c_int(oth), _ptr(cp), _ptr(nc), _ptr(w), C.c_int64(len(w))))
+
+
+Context.batch_set_pair_matches = _batch_set_pair_matches
 Context.batch_declare_pairs = _batch_declare_pairs
 Context.batch_solve = _batch_solve
 Context.set_allreduce = _set_allreduce

@@ -1157,6 +1157,34 @@ int glio_batch_declare_pairs(glio_ctx* c, const int32_t* pairs_cur, const int32_
   });
 }
 
+int glio_batch_set_pair_matches(glio_ctx* c, int cur, int oth, const float* cp, const double* normal_cent, const float* weight, int64_t n) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(cur >= 0 && oth >= 0 && cur != oth, GLIO_ERR_ARG, "bad pair");
+    GLIO_REQUIRE(n >= 0 && (n == 0 || (cp && normal_cent && weight)), GLIO_ERR_ARG, "null match arrays");
+    const std::pair<int, int> key(cur, oth);
+    auto it = c->pair_index.find(key);
+    int pi;
+    if (it == c->pair_index.end()) {
+      pi = (int)c->pairs.size(); c->pair_index[key] = pi;
+      c->pairs.emplace_back(new glio_ctx::Pair()); c->pairs.back()->cur = cur; c->pairs.back()->oth = oth;
+    } else pi = it->second;
+    glio_ctx::Pair& pr = *c->pairs[pi];
+    pr.n_match = n; pr.n_sel = -1;
+    if (n > 0) {
+      std::vector<float> cpw((size_t)n * 4);
+      std::vector<int32_t> src((size_t)n);
+      for (int64_t i = 0; i < n; ++i) { cpw[4 * i] = cp[3 * i]; cpw[4 * i + 1] = cp[3 * i + 1]; cpw[4 * i + 2] = cp[3 * i + 2]; cpw[4 * i + 3] = weight[i]; src[i] = (int32_t)i; }
+      pr.m_cpw.reserve((size_t)n); pr.m_nc.reserve((size_t)n * 6); pr.m_src.reserve((size_t)n);
+      GLIO_CUDA_TRY(cudaMemcpyAsync(pr.m_cpw.p, cpw.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->st));
+      GLIO_CUDA_TRY(cudaMemcpyAsync(pr.m_nc.p, normal_cent, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, c->st));
+      GLIO_CUDA_TRY(cudaMemcpyAsync(pr.m_src.p, src.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->st));
+      GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    }
+    c->bin_dirty = true;
+  });
+}
+
 int glio_batch_solve(glio_ctx* c, int K, double* poses, double* speed_bias, glio_host_factors_band_fn host_factors, void* user,
                      const glio_solver_options* options, glio_solver_summary* summary, glio_iteration* iter_log, int iter_cap,
                      double* step_log, int64_t step_cap) {

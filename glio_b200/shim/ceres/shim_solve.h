@@ -65,6 +65,11 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
   std::vector<Slot> slots;
   std::map<std::pair<double*, double*>, int> slot_of;
   std::vector<const Problem::Residual*> host_blocks;
+  struct BPair { int kc, ko; std::vector<float> cp; std::vector<double> nc; std::vector<float> w; };
+  std::vector<BPair> bpairs;                                     // in creation order == glio_batch_pair_list order
+  std::map<std::pair<int, int>, int> bpair_of;
+  std::vector<std::pair<double*, double*>> bkfs;                 // keyframes (t, q blocks) touched by binary factors
+  std::map<std::pair<double*, double*>, int> bkf_of;
   glio_ctx* ctx = problem->ctx_;
   glio_params gp;
   if (ctx && glio_get_params(ctx, &gp) != GLIO_OK) ctx = nullptr;
@@ -72,7 +77,9 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
     const Problem::Residual* rb = rbp.get();
     glio::FactorDesc d;
     bool dev = false;
-    if (ctx && rb->cost->GlioDescribe(&d) && d.kind == glio::FACTOR_PLANE_UNARY && rb->params.size() == 2) {
+    const bool described = ctx && rb->cost->GlioDescribe(&d);
+    if (!described) d.kind = glio::FACTOR_NONE;
+    if (described && d.kind == glio::FACTOR_PLANE_UNARY && rb->params.size() == 2) {
       double* t = rb->params[0]; double* q = rb->params[1];
       const HuberLoss* hl = dynamic_cast<const HuberLoss*>(rb->loss);
       const bool loss_ok = (rb->loss == nullptr && gp.huber_delta <= 0) || (hl && hl->a() == gp.huber_delta);
@@ -96,9 +103,48 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
         dev = true;
       }
     }
+    // BinaryLidarPlaneNormFactor (LidarKeyframeFactor.h:124-164): four blocks (t_cur, q_cur, t_oth, q_oth), no loss
+    // (Estimator.cpp:2768); grouped by keyframe pair and evaluated by K2b
+    if (!dev && ctx && d.kind == glio::FACTOR_PLANE_BINARY && rb->params.size() == 4 && rb->loss == nullptr && gp.batch_score != 0.0) {
+      double* tc = rb->params[0]; double* qc = rb->params[1]; double* to = rb->params[2]; double* qo = rb->params[3];
+      auto blk_ok = [&](double* t, double* q) {
+        return P.index.count(t) && P.index.count(q) && problem->blocks_.at(t).size == 3 && problem->blocks_.at(q).size == 4 &&
+               dynamic_cast<QuaternionParameterization*>(problem->blocks_.at(q).param) != nullptr;
+      };
+      const double w = d.score / gp.batch_score;
+      const bool repr = is_f32(w) && gp.batch_score * (double)(float)w == d.score && is_f32(d.cp[0]) && is_f32(d.cp[1]) && is_f32(d.cp[2]);
+      if (blk_ok(tc, qc) && blk_ok(to, qo) && !(tc == to && qc == qo) && repr) {
+        auto kf_of = [&](double* t, double* q) {
+          auto key = std::make_pair(t, q);
+          auto it = bkf_of.find(key);
+          if (it != bkf_of.end()) return it->second;
+          const int k = (int)bkfs.size(); bkf_of[key] = k; bkfs.push_back(key); return k;
+        };
+        const int kc = kf_of(tc, qc), ko = kf_of(to, qo);
+        auto pkey = std::make_pair(kc, ko);
+        auto pit = bpair_of.find(pkey);
+        int pi;
+        if (pit == bpair_of.end()) { pi = (int)bpairs.size(); bpair_of[pkey] = pi; bpairs.push_back(BPair{kc, ko, {}, {}, {}}); } else pi = pit->second;
+        BPair& bp = bpairs[pi];
+        for (int k = 0; k < 3; ++k) bp.cp.push_back((float)d.cp[k]);
+        for (int k = 0; k < 6; ++k) bp.nc.push_back(d.nc[k]);
+        bp.w.push_back((float)w);
+        dev = true;
+      }
+    }
     if (!dev) host_blocks.push_back(rb);
   }
   const int W = (int)slots.size();
+  const int KB = (int)bkfs.size(), PB = (int)bpairs.size();
+  if (PB > 0) {
+    if (glio_batch_clear(ctx) != GLIO_OK) { S.termination_type = FAILURE; S.message = std::string("glio_batch_clear: ") + glio_last_error(ctx); return; }
+    for (int p = 0; p < PB; ++p) {
+      if (glio_batch_set_pair_matches(ctx, bpairs[p].kc, bpairs[p].ko, bpairs[p].cp.data(), bpairs[p].nc.data(), bpairs[p].w.data(), (int64_t)bpairs[p].w.size()) != GLIO_OK) {
+        S.termination_type = FAILURE; S.message = std::string("glio_batch_set_pair_matches: ") + glio_last_error(ctx); return;
+      }
+      S.num_device_residual_blocks += (int)bpairs[p].w.size();
+    }
+  }
   for (int k = 0; k < W; ++k) {
     if (glio_set_matches(ctx, k, slots[k].cp.data(), slots[k].nsd.data(), slots[k].w.data(), (int64_t)slots[k].w.size()) != GLIO_OK) {
       S.termination_type = FAILURE; S.message = std::string("glio_set_matches: ") + glio_last_error(ctx); return;
@@ -138,6 +184,7 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
   std::vector<double> x(P.n_amb);
   for (const ActiveBlock& a : P.active) std::memcpy(&x[a.amb_off], a.user, sizeof(double) * a.size);
   std::vector<double> poses((size_t)std::max(W, 1) * 7), Hd((size_t)std::max(W, 1) * 36), gd((size_t)std::max(W, 1) * 6), cd(std::max(W, 1));
+  std::vector<double> bposes((size_t)std::max(KB, 1) * 7), bHd((size_t)std::max(KB, 1) * 36), bHo((size_t)std::max(PB, 1) * 36), bg((size_t)std::max(KB, 1) * 6);
   double fixed_cost = 0; bool fixed_done = false;
 
   glio::EvalFn eval = [&](const double* xa, bool want_jac, double* cost, glio::BandMat* H, double* g) -> bool {
@@ -160,6 +207,31 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
           g[ip] += gd[6 * k + p];
           for (int q = 0; q < 6; ++q) { const int iq = off[q / 3] + q % 3; if (ip >= iq) H->at(ip, iq) += Hd[36 * k + 6 * p + q]; }
         }
+      }
+    }
+    if (PB > 0) {
+      for (int k = 0; k < KB; ++k) {
+        const ActiveBlock& at = P.active[P.index[bkfs[k].first]]; const ActiveBlock& aq = P.active[P.index[bkfs[k].second]];
+        for (int i = 0; i < 3; ++i) bposes[7 * k + i] = xa[at.amb_off + i];
+        for (int i = 0; i < 4; ++i) bposes[7 * k + 3 + i] = xa[aq.amb_off + i];
+      }
+      double bc = 0;
+      if (glio_eval_binary(ctx, KB, bposes.data(), want_jac ? bHd.data() : nullptr, want_jac ? bHo.data() : nullptr, want_jac ? bg.data() : nullptr, &bc) != GLIO_OK) return false;
+      ct += bc;
+      if (want_jac) {
+        auto toff = [&](int kf, int p) { return (p < 3 ? P.active[P.index[bkfs[kf].first]].tan_off : P.active[P.index[bkfs[kf].second]].tan_off) + p % 3; };
+        for (int k = 0; k < KB; ++k)
+          for (int p = 0; p < 6; ++p) {
+            const int ip = toff(k, p);
+            g[ip] += bg[6 * k + p];
+            for (int q = 0; q < 6; ++q) { const int iq = toff(k, q); if (ip >= iq) H->at(ip, iq) += bHd[36 * k + 6 * p + q]; }
+          }
+        for (int pr = 0; pr < PB; ++pr)                       // block (cur, oth): row = cur tangent, col = oth tangent; lower triangle holds it once
+          for (int p = 0; p < 6; ++p) for (int q = 0; q < 6; ++q) {
+            const int ip = toff(bpairs[pr].kc, p), iq = toff(bpairs[pr].ko, q);
+            const double v = bHo[36 * pr + 6 * p + q];
+            if (ip >= iq) H->at(ip, iq) += v; else H->at(iq, ip) += v;
+          }
       }
     }
     // host blocks (ResidualBlock::Evaluate, ceres.tgz::internal/ceres/residual_block.cc:70-197)

@@ -269,6 +269,11 @@ int glio_batch_clear(glio_ctx* ctx);
  * buffers have one layout everywhere. */
 int glio_batch_declare_pairs(glio_ctx* ctx, const int32_t* pairs_cur, const int32_t* pairs_oth, int64_t n_pairs);
 
+/* Upload the matches of pair (cur, oth) instead of associating them (creates the pair when it does not exist yet) - the
+ * path the Ceres-API shim takes for BinaryLidarPlaneNormFactor residual blocks, which carry their own data
+ * (LidarKeyframeFactor.h:161-163: curr_point, planet_norm_cent, score = batch_score*weight). */
+int glio_batch_set_pair_matches(glio_ctx* ctx, int cur, int oth, const float* cp, const double* normal_cent, const float* weight, int64_t n);
+
 /* ---- K2b: evaluate all active binary plane residuals at poses[K*7].
  * Replaces ResidualBlock::Evaluate over BinaryLidarPlaneNormFactor (LidarKeyframeFactor.h:124-164; no loss function,
  * Estimator.cpp:2768) and the J^T J / J^T r accumulation.  Block-sparse output: Hdiag[K*36], Hoff[n_pairs*36]

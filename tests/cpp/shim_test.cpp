@@ -54,6 +54,38 @@ template <> struct DeviceFactorTraits<LidarPlaneNormFactor> {
 };
 }  // namespace glio
 
+// Eigen-free transcription of the reference's BinaryLidarPlaneNormFactor::operator() (LidarKeyframeFactor.h:132-150)
+struct BinaryLidarPlaneNormFactor {
+  BinaryLidarPlaneNormFactor(const double* cp_, const double* nc_, double s_) : score(s_) {
+    for (int k = 0; k < 3; ++k) curr_point[k] = cp_[k];
+    for (int k = 0; k < 6; ++k) planet_norm_cent[k] = nc_[k];
+  }
+  template <typename T> bool operator()(const T* t1, const T* q1, const T* t2, const T* q2, T* residual) const {
+    T cp[3] = {T(curr_point[0]), T(curr_point[1]), T(curr_point[2])};
+    T nl[3] = {T(planet_norm_cent[0]), T(planet_norm_cent[1]), T(planet_norm_cent[2])}, cl[3] = {T(planet_norm_cent[3]), T(planet_norm_cent[4]), T(planet_norm_cent[5])};
+    T pw[3], no[3], co[3];
+    QuatRotate(q1, cp, pw); QuatRotate(q2, nl, no); QuatRotate(q2, cl, co);
+    for (int k = 0; k < 3; ++k) { pw[k] = pw[k] + t1[k]; co[k] = co[k] + t2[k]; }
+    residual[0] = T(score) * (no[0] * (pw[0] - co[0]) + no[1] * (pw[1] - co[1]) + no[2] * (pw[2] - co[2]));
+    return true;
+  }
+  static ceres::CostFunction* Create(const double* cp, const double* nc, double s) {
+    return new ceres::AutoDiffCostFunction<BinaryLidarPlaneNormFactor, 1, 3, 4, 3, 4>(new BinaryLidarPlaneNormFactor(cp, nc, s));
+  }
+  double curr_point[3], planet_norm_cent[6], score;
+};
+namespace glio {
+template <> struct DeviceFactorTraits<BinaryLidarPlaneNormFactor> {
+  static bool describe(const BinaryLidarPlaneNormFactor& f, FactorDesc* d) {
+    d->kind = FACTOR_PLANE_BINARY;
+    for (int k = 0; k < 3; ++k) d->cp[k] = f.curr_point[k];
+    for (int k = 0; k < 6; ++k) d->nc[k] = f.planet_norm_cent[k];
+    d->score = f.score;
+    return true;
+  }
+};
+}  // namespace glio
+
 // stand-ins for the host factors (IMU-chain-like / prior-like / pseudorange-like), autodiff on the host
 struct PriorF {
   double t0[3], q0[4], sb0[9], sw[15];
@@ -165,6 +197,17 @@ int main(int argc, char** argv) {
     for (int i = 0; i < nrg; ++i) {
       int32_t k; RangeF* p = new RangeF(); rd(f, &k, 1); rd(f, p->lever, 3); rd(f, p->sat, 3); rd(f, &p->rho, 1); rd(f, &p->w, 1);
       problem.AddResidualBlock(new ceres::AutoDiffCostFunction<RangeF, 1, 3, 4>(p), NULL, tmpTrans[k], tmpQuat[k]);
+    }
+    // optional trailing section: scan-to-multiscan (binary) plane factors between keyframes of the same problem,
+    // added the way optimizeBatchWithLandMark does (Estimator.cpp:3049-3051, :3073-3074: loss == NULL, four blocks)
+    int32_t nbin = 0;
+    if (rd(f, &nbin, 1) && nbin > 0) {
+      std::vector<int32_t> kc(nbin), ko(nbin); std::vector<float> bcp(3 * (size_t)nbin); std::vector<double> bnc(6 * (size_t)nbin), bsc(nbin);
+      rd(f, kc.data(), nbin); rd(f, ko.data(), nbin); rd(f, bcp.data(), bcp.size()); rd(f, bnc.data(), bnc.size()); rd(f, bsc.data(), nbin);
+      for (int i = 0; i < nbin; ++i) {
+        const double c[3] = {bcp[3 * i], bcp[3 * i + 1], bcp[3 * i + 2]};
+        problem.AddResidualBlock(BinaryLidarPlaneNormFactor::Create(c, &bnc[6 * (size_t)i], bsc[i]), NULL, tmpTrans[kc[i]], tmpQuat[kc[i]], tmpTrans[ko[i]], tmpQuat[ko[i]]);
+      }
     }
     fclose(f);
     ceres::Solver::Options options;                                                        // Estimator.cpp:2424-2430

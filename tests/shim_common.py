@@ -17,7 +17,7 @@ def build_shim_test(tmpdir):
     return exe
 
 
-def write_problem(path, poses, sb, q_lb, t_lb, lidar_const, huber, kf, cp, nsd, w, priors, betweens, ranges):
+def write_problem(path, poses, sb, q_lb, t_lb, lidar_const, huber, kf, cp, nsd, w, priors, betweens, ranges, binary=None):
     W = len(poses)
     with open(path, "wb") as f:
         f.write(struct.pack("<ii", W, 1 if sb is not None else 0))
@@ -40,6 +40,12 @@ def write_problem(path, poses, sb, q_lb, t_lb, lidar_const, huber, kf, cp, nsd, 
         for (k, lever, sat, rho, w_) in ranges:
             f.write(struct.pack("<i", k)); f.write(np.asarray(lever, np.float64).tobytes()); f.write(np.asarray(sat, np.float64).tobytes())
             f.write(struct.pack("<dd", rho, w_))
+        if binary is not None:
+            kc, ko, bcp, bnc, bsc = binary
+            f.write(struct.pack("<i", len(kc)))
+            f.write(np.ascontiguousarray(kc, np.int32).tobytes()); f.write(np.ascontiguousarray(ko, np.int32).tobytes())
+            f.write(np.ascontiguousarray(bcp, np.float32).tobytes()); f.write(np.ascontiguousarray(bnc, np.float64).tobytes())
+            f.write(np.ascontiguousarray(bsc, np.float64).tobytes())
 
 
 def run_shim(exe, path, mode):
@@ -86,9 +92,31 @@ def make_problem(oracle, synth, W=4, Q=800, M=20000, seed=17, n_sel=150):
     return P, kf, cp, nsd, w, sb0, priors, betweens, ranges
 
 
-def oracle_solve(oracle, P, kf, cp, nsd, w, sb0, priors, betweens, ranges, lidar_const=7.5):
+def make_binary(oracle, synth, P, pairs=((0, 1), (1, 0), (2, 1), (3, 2), (1, 3)), n_sel=120, batch_score=2.5, Qb=5000):
+    """Scan-to-multiscan matches between keyframes of the window problem, from the ORACLE pair association.  The batch
+    path applies the keyframe poses directly to the stored scan points (quirk Q7), so denser body-frame scans of the
+    same scene / trajectory are drawn here (same RNG order as synth.window_problem rebuilds scene and truth)."""
+    rng = np.random.default_rng(P["seed"])
+    scene = synth.Scene(-60.0, P["W"] + 60.0, rng, n_boxes=30)
+    truth = synth.trajectory(P["W"], rng)
+    assert np.array_equal(truth, P["poses_true"])
+    r2 = np.random.default_rng(P["seed"] + 1000)
+    scans = [synth.scan_in_body_frame(scene, truth[k], Qb, r2, rng_range=12.0) for k in range(P["W"])]
+    kc, ko, cp, nc, sc = [], [], [], [], []
+    for (c, o) in pairs:
+        a = oracle.assoc_pair(scans[c], P["poses_init"][c, :3], P["poses_init"][c, 3:], scans[o], P["poses_init"][o, :3], P["poses_init"][o, 3:])
+        v = np.nonzero(a["status"] == 0)[0][:n_sel]
+        assert len(v) > 20, len(v)
+        kc.append(np.full(len(v), c, np.int32)); ko.append(np.full(len(v), o, np.int32)); cp.append(scans[c][v])
+        nc.append(a["normal_cent"][v]); sc.append(batch_score * a["weight"][v].astype(np.float64))
+    return tuple(map(np.concatenate, (kc, ko, cp, nc, sc)))
+
+
+def oracle_solve(oracle, P, kf, cp, nsd, w, sb0, priors, betweens, ranges, lidar_const=7.5, binary=None):
     prob = oracle.WindowProblem(P["poses_init"], sb0, P["q_lb"], P["t_lb"], huber_delta=1.0)
     prob.add_unary(kf, cp, nsd, lidar_const * w.astype(np.float64))
+    if binary is not None:
+        prob.add_binary(*binary)
     for a in priors: prob.add_prior(*a)
     for a in betweens: prob.add_between(*a)
     for a in ranges: prob.add_range(*a)

@@ -143,3 +143,25 @@ def _compare_batch_solves(ctx, oracle, api, B, prob_template, hf, K, radius0):
         assert ig["cost"] == pytest.approx(io["cost"], rel=1e-9)
     assert np.max(np.abs(rg["poses"] - ro["poses"])) <= 1e-6
     assert sg.final_cost < sg.initial_cost
+
+
+def test_uploaded_pair_matches_equal_associated_ones(setup):
+    """glio_batch_set_pair_matches (the path the Ceres shim takes for BinaryLidarPlaneNormFactor blocks): a second
+    context fed with the downloaded matches of the first evaluates to the same blocks."""
+    from glio_b200 import api
+    ctx, B, cur, oth, nm = setup
+    pc, po_ = ctx.batch_pair_list()
+    g1 = ctx.eval_binary(B["poses_init"])
+    c2 = api.Context(0)
+    try:
+        for c, o in zip(pc, po_):
+            m = ctx.batch_get_matches(int(c), int(o), B["Q"])
+            c2.batch_set_pair_matches(int(c), int(o), m["cp"], m["normal_cent"], m["weight"])
+        p2c, p2o = c2.batch_pair_list()
+        assert np.array_equal(p2c, pc) and np.array_equal(p2o, po_)
+        g2 = c2.eval_binary(B["poses_init"])
+        for k in ("Hdiag", "Hoff", "g"):
+            assert np.allclose(g2[k], g1[k], rtol=1e-13, atol=0), k
+        assert abs(g2["cost"] - g1["cost"]) <= 1e-13 * g1["cost"]
+    finally:
+        c2.close()

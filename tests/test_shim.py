@@ -43,3 +43,28 @@ def test_shim_device_routing_matches_oracle(tmp_path, oracle):
     res = sc.run_shim(exe, path, "device")
     assert res["device_blocks"] == len(kf)                 # every LidarPlaneNormFactor block ran on the GPU
     _check(res, ro, 4)
+
+
+def _binary_case(tmp_path, oracle, mode):
+    exe = sc.build_shim_test(tmp_path)
+    P, kf, cp, nsd, w, sb0, priors, betweens, ranges = sc.make_problem(oracle, synth)
+    binary = sc.make_binary(oracle, synth, P)
+    path = str(tmp_path / "pb.bin")
+    sc.write_problem(path, P["poses_init"], sb0, P["q_lb"], P["t_lb"], 7.5, 1.0, kf, cp, nsd, w, priors, betweens, ranges, binary=binary)
+    ro = sc.oracle_solve(oracle, P, kf, cp, nsd, w, sb0, priors, betweens, ranges, binary=binary)
+    res = sc.run_shim(exe, path, mode)
+    return res, ro, len(kf), len(binary[0])
+
+
+def test_shim_host_only_with_binary_factors(tmp_path, oracle):
+    res, ro, nu, nb = _binary_case(tmp_path, oracle, "host")
+    assert res["device_blocks"] == 0
+    _check(res, ro, 4)
+
+
+@pytest.mark.gpu
+def test_shim_device_routing_with_binary_factors(tmp_path, oracle):
+    """LidarPlaneNormFactor AND BinaryLidarPlaneNormFactor blocks of one problem both run on the GPU (K2 + K2b)."""
+    res, ro, nu, nb = _binary_case(tmp_path, oracle, "device")
+    assert res["device_blocks"] == nu + nb
+    _check(res, ro, 4)
