@@ -293,16 +293,19 @@ def run_glio(args, rank, world, local_rank):
         alg = 116.0 * Qt + 12.0 * CFG["M"]
         ach = alg / (avg_ms * 1e-3) / 1e9
         # DRAM traffic of the same two kernels from the committed ncu --set full captures (bytes per launch, cfg 2 sizes)
-        traffic, traffic_src = None, None
+        traffic, traffic_src, issue = None, None, None
         try:
             tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
             if "k_knn_box" in tj and "k_plane_fit" in tj and "k_knn_box" in prof:
-                traffic = float(tj["k_knn_box"] + tj["k_plane_fit"]); traffic_src = tj.get("_source")
+                traffic = float(tj["k_knn_box"]["dram_bytes"] + tj["k_plane_fit"]["dram_bytes"]); traffic_src = tj.get("_source")
+                kb = tj["k_knn_box"]
+                issue = dict(kernel="k_knn_box", warp_instructions=kb["warp_inst"], issue_active_pct=kb["issue_active_pct"], active_threads_per_instruction=kb["threads_per_inst"],
+                             note="the association pass is bound by instruction issue, not HBM: see DESIGN.md section 4 and profiles/r01_knn_box_sass_regions.txt")
         except Exception:
             pass
         roof = dict(bound="hbm", kernel="K1 association pass = k_knn_box + k_plane_fit (exact 5-NN + plane fit + gates)",
                     achieved=round(ach, 2), peak=peak, unit="GB/s", frac=round(ach / peak, 5), traffic=traffic, algorithmic_bytes=alg,
-                    avg_ms=round(avg_ms, 5), peak_source=peak_src, traffic_source=traffic_src)
+                    avg_ms=round(avg_ms, 5), peak_source=peak_src, traffic_source=traffic_src, issue_bound_evidence=issue)
     if "k_eval_unary" in prof and prof["k_eval_unary"][1] > 0:
         avg_ms2 = prof["k_eval_unary"][0] / prof["k_eval_unary"][1]
         nres = int(rlast["summary"].num_iterations and sum(ctx.get_match_counts(W)))

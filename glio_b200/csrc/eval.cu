@@ -108,8 +108,11 @@ __device__ __forceinline__ void unary_accumulate(const float4 c4, const float4 n
 // poses of up to EV_MAXW keyframes travel in the kernel parameters (no host-to-device copy on the per-iteration path)
 struct PoseArgs { double p[EV_MAXW * 7]; };
 
+#ifndef GLIO_EVAL_MINBLOCKS
+#define GLIO_EVAL_MINBLOCKS 2
+#endif
 template <bool WANT_JAC, int JAC_KIND, bool POSE_ARGS>
-__global__ void __launch_bounds__(EV_T, 2) k_eval_unary(const EvalItem* __restrict__ items, int nitems, int W,
+__global__ void __launch_bounds__(EV_T, GLIO_EVAL_MINBLOCKS) k_eval_unary(const EvalItem* __restrict__ items, int nitems, int W,
                                                         const double* __restrict__ poses, const __grid_constant__ PoseArgs pa, EvalParams ep,
                                                         double* __restrict__ partials, double* __restrict__ out,
                                                         const int* __restrict__ kf_item_start, unsigned int* __restrict__ ticket,

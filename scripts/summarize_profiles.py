@@ -60,20 +60,21 @@ def _traffic(rep):
     rows = list(csv.reader(out.splitlines()))
     if len(rows) < 3: return {}
     h, u = rows[0], rows[1]; res = {}
+    def num(r, m):
+        return float(r[h.index(m)].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u[h.index(m)], 1)
     for r in rows[2:]:
         name = re.sub(r"^(void )?(glio::)?", "", r[h.index("Kernel Name")]); name = re.sub(r"[<(].*$", "", name)
-        tot = 0.0
-        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            tot += float(r[h.index(m)].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u[h.index(m)], 1)
-        res.setdefault(name, []).append(tot)
-    return {k: sum(v) / len(v) for k, v in res.items()}
+        e = res.setdefault(name, dict(dram_bytes=[], warp_inst=[], issue_active_pct=[], threads_per_inst=[], time_us=[]))
+        e["dram_bytes"].append(num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum"))
+        e["warp_inst"].append(num(r, "smsp__inst_executed.sum")); e["issue_active_pct"].append(num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"))
+        e["threads_per_inst"].append(num(r, "smsp__thread_inst_executed_per_inst_executed.ratio")); e["time_us"].append(num(r, "gpu__time_duration.sum"))
+    return {k: {m: round(sum(v) / len(v), 2) for m, v in e.items()} for k, e in res.items()}
 tr = {}
 for rep in ("prof_top.ncu-rep",):
     if os.path.exists(os.path.join(G, rep)): tr.update(_traffic(os.path.join(G, rep)))
 if tr:
-    tr = {k: round(v) for k, v in tr.items()}
-    tr["_source"] = "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum per launch, cfg 2 sizes (gpurun_out/prof_top.ncu-rep of round %s, mean over the captured launches)" % rnd[1:]
-    json.dump(tr, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1); print("wrote ncu_traffic.json", tr)
+    tr["_source"] = "ncu --set full --clock-control none per launch, cfg 2 sizes (gpurun_out/prof_top.ncu-rep of round %s, mean over the captured launches); dram_bytes = dram__bytes_read.sum + dram__bytes_write.sum" % rnd[1:]
+    json.dump(tr, open(os.path.join(P, "ncu_traffic.json"), "w"), indent=1); print("wrote ncu_traffic.json", {k: v for k, v in tr.items() if k != "_source"})
 
 for name in ("bench_line.json", "bench_reference_line.json"):
     s = os.path.join(G, name)
