@@ -73,3 +73,27 @@ def test_batch_pair_enumeration_matches_reference_rule():
         assert js == [j for j in range(s, s + 7) if j != idx]
     own = dist.owner_of(cur, 20, 4)
     assert sorted(set(own.tolist())) == [0, 1, 2, 3] and (np.diff(own[np.argsort(cur, kind="stable")]) >= 0).all()
+
+
+def test_null_context_is_an_argument_error_not_a_crash():
+    """Error convention of the ABI: every entry point returns a negative glio_status, nothing aborts."""
+    lib = ctypes.CDLL(os.path.join(ROOT, "glio_b200", "libglio_b200.so"))
+    n = ctypes.c_void_p(None)
+    z = ctypes.c_int64(0)
+    calls = [
+        ("glio_set_map", (n, n, z, ctypes.c_int(3), ctypes.c_int(0))),
+        ("glio_window_set_scans", (n, ctypes.c_int(1), n, n, ctypes.c_int(3), ctypes.c_int(0))),
+        ("glio_window_associate", (n, ctypes.c_int(1), n, n)),
+        ("glio_eval_unary", (n, ctypes.c_int(1), n, ctypes.c_int(0), n, n, n)),
+        ("glio_eval_binary", (n, ctypes.c_int(1), n, n, n, n, n)),
+        ("glio_batch_set_pair_matches", (n, ctypes.c_int(0), ctypes.c_int(1), n, n, n, z)),
+        ("glio_localmap_clear", (n,)),
+        ("glio_localmap_push", (n, ctypes.c_int(0), n, z, ctypes.c_int(3), ctypes.c_int(0), n, n)),
+        ("glio_localmap_pop_front", (n,)),
+        ("glio_localmap_build", (n, ctypes.c_float(0.4), n)),
+        ("glio_get_map", (n, z, n, n)),
+        ("glio_synchronize", (n,)),
+    ]
+    for name, args in calls:
+        f = getattr(lib, name); f.restype = ctypes.c_int
+        assert f(*args) == -3, name          # GLIO_ERR_ARG
