@@ -6,6 +6,7 @@ import re
 
 import numpy as np
 import pytest
+import torch  # noqa: F401  (first: torch must bind its bundled CUDA runtime before libglio_b200.so pulls in the system libcudart)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
