@@ -5,6 +5,7 @@
 // r(x) = J x + r0 with the fixture's options (min_lm_diagonal = max_lm_diagonal = 1: no diagonal scaling; the test
 // drives the strategy directly, so the minimizer-level Jacobi scaling is off).
 // Prints "name ok|FAIL detail" lines; tests/test_dogleg_known_answers.py asserts on them.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <limits>
@@ -98,6 +99,27 @@ static bool powell_case(bool c1, bool c2, bool c3, bool c4, double out[4]) {
   return ok;
 }
 
+// ---- ceres.tgz::internal/ceres/polynomial_test.cc:144-210: FindPolynomialRoots known answers for the degrees the
+// subspace dogleg uses (<= 4), against glio::detail::real_roots_deg4 (real parts; complex pairs give their real part twice,
+// which is what dogleg_strategy.cc:473-507 consumes).  Tolerances and the relative/absolute rule are Ceres' ExpectClose.
+static std::vector<double> add_root(const std::vector<double>& p, double r) {
+  std::vector<double> q(p.size() + 1, 0.0);
+  for (size_t i = 0; i < p.size(); ++i) { q[i] += p[i]; q[i + 1] -= r * p[i]; }
+  return q;
+}
+static double rel_diff(double x, double y) { const double a = std::fabs(x - y); return (x == 0 || y == 0) ? a : a / std::max(std::fabs(x), std::fabs(y)); }
+static void poly_case(const char* name, std::vector<double> roots, double eps) {
+  std::vector<double> p{1.23};
+  for (double r : roots) p = add_root(p, r);
+  double poly5[5] = {0, 0, 0, 0, 0};
+  for (size_t i = 0; i < p.size(); ++i) poly5[5 - p.size() + i] = p[i];
+  std::vector<double> got;
+  bool ok = glio::detail::real_roots_deg4(poly5, &got) && got.size() == roots.size();
+  std::sort(got.begin(), got.end()); std::sort(roots.begin(), roots.end());
+  for (size_t i = 0; ok && i < roots.size(); ++i) ok = rel_diff(got[i], roots[i]) <= eps;
+  report(name, ok, got);
+}
+
 int main() {
   const double kEps = std::numeric_limits<double>::epsilon(), kLoose = 1e-5;
   // DoglegStrategyFixtureEllipse (dogleg_strategy_test.cc:60-91): J^T J = Q diag(1,2,4,8,16,32) Q^T, minimum at (1,...,1)
@@ -138,6 +160,17 @@ int main() {
     const bool ok = powell_case(cases[c][0], cases[c][1], cases[c][2], cases[c][3], out);
     char name[64]; snprintf(name, sizeof(name), "Powell_%d%d%d%d", (int)cases[c][0], (int)cases[c][1], (int)cases[c][2], (int)cases[c][3]);
     report(name, ok, std::vector<double>(out, out + 4));
+  }
+  poly_case("Poly_LinearPositive", {42.42}, 1e-13); poly_case("Poly_LinearNegative", {-42.42}, 1e-13);
+  poly_case("Poly_QuadraticPositive", {1.0, 42.42}, 1e-13); poly_case("Poly_QuadraticOneNegative", {-42.42, 1.0}, 1e-13);
+  poly_case("Poly_QuadraticTwoNegative", {-42.42, -1.0}, 1e-13); poly_case("Poly_QuadraticClose", {42.42, 42.43}, 1e-9);
+  poly_case("Poly_Quartic", {1.23e-4, 1.23e-1, 1.23e+2, 1.23e+5}, 1e-13); poly_case("Poly_QuarticTwoClusters", {1.23e-1, 2.46e-1, 1.23e+5, 2.46e+5}, 1e-9);
+  poly_case("Poly_QuarticTwoZeroRoots", {-42.42, 0.0, 0.0, 42.42}, 2e-9); poly_case("Poly_QuarticMonomial", {0.0, 0.0, 0.0, 0.0}, 1e-13);
+  {  // QuadraticPolynomialWithComplexRootsWorks (:174-190): 42.42 +- 4.2i -> real parts 42.42, 42.42
+    const double poly5[5] = {0, 0, 1.23, -2 * 42.42 * 1.23, (42.42 * 42.42 + 4.2 * 4.2) * 1.23};
+    std::vector<double> got; bool ok = glio::detail::real_roots_deg4(poly5, &got) && got.size() == 2;
+    for (size_t i = 0; ok && i < 2; ++i) ok = rel_diff(got[i], 42.42) <= 1e-13;
+    report("Poly_QuadraticComplexPair", ok, got);
   }
   return 0;
 }
