@@ -4,8 +4,10 @@
 // findGlobalCorrespondingSurfFeatures[Add]_Batch (Estimator.cpp:3710-3892):
 //   transform -> exact 5-NN (FLANN L2_Simple<float> distances, ties by index) -> gate on the squared 5th
 //   distance -> 5x3 column-pivoted Householder LS plane fit (double) -> validity -> weight -> outputs.
-// Exactness of the kNN: rings of grid cells are searched until the 5th best distance is provably inside the
-// searched cube, or the cube already covers the gate radius (then anything unseen fails the gate anyway).
+// Exactness of the kNN: a box of grid cells around the query is searched and grown (face by face in the default
+// k_knn_box, ring by ring in k_knn_thread / the warp-cooperative k_knn_search kept for comparison, GLIO_KNN_MODE) until
+// the 5th best distance is provably inside the searched box, or the box already covers the gate radius (then anything
+// unseen fails the gate anyway).
 //
 // This translation unit is compiled with -fmad=false (see Makefile) in addition to the explicit *_rn
 // intrinsics of devmath.cuh: kNN indices and the valid mask must be bit-exact w.r.t. the no-FMA reference.
@@ -86,7 +88,7 @@ __device__ __forceinline__ void top5_push(Top5& t, float d, int id) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K1a: warp-cooperative exact 5-NN.
+// K1a (warp-cooperative variant, GLIO_KNN_MODE=0; not the default - see DESIGN.md section 4 for the measurements).
 // Queries arrive sorted by grid cell, so the 32 queries of a warp sit in a short run of x-adjacent cells of one
 // (y,z) row.  The warp stages the rows around that run — each row is ONE contiguous range of the counting-sorted
 // map (x is the fastest cell coordinate) — through shared memory with coalesced 16-byte loads, and every lane scans
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K1a (per-thread variant): one query per thread, rings of cells around the query's own cell, each (y,z) row of a
+// K1a (per-thread variants, GLIO_KNN_MODE=1..3): one query per thread, rings of cells around the query's own cell, each (y,z) row of a
 // ring is one contiguous range of the sorted map.  Fewer candidate evaluations per query than the tile pass (the
 // searched box is exactly the query's own), at the price of divergent trip counts.  Queries arrive cell-sorted, so
 // the loads of neighbouring threads hit the same lines.
