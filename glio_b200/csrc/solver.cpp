@@ -325,6 +325,8 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval_user, SolverSumma
     } else ++S.num_unsuccessful_steps;
     it.trust_region_radius = radius; it.mu = mu;
     S.iterations.push_back(it);
+    // trust_region_minimizer.cc:327-333, :605-619 (MaxSolverTimeReached, checked before the iteration limit): wall clock since the start of the solve
+    if (std::chrono::duration<double>(clk::now() - t_begin).count() >= opt_.max_solver_time_in_seconds) { S.termination = TERM_NO_CONVERGENCE; S.message = "Maximum solver time reached."; return false; }
     if (it.iteration >= opt_.max_num_iterations) { S.termination = TERM_NO_CONVERGENCE; S.message = "Maximum number of iterations reached."; return false; }
     if (it.step_is_successful && it.gradient_max_norm <= opt_.gradient_tolerance) { S.termination = TERM_CONVERGENCE; S.message = "Gradient tolerance reached."; return false; }
     if (radius <= opt_.min_trust_region_radius) { S.termination = TERM_CONVERGENCE; S.message = "Minimum trust region radius reached."; return false; }

@@ -31,6 +31,7 @@ struct ParamBlock {
 
 struct SolverOptions {
   int max_num_iterations = 15;
+  double max_solver_time_in_seconds = 1e9;   // Solver::Options::max_solver_time_in_seconds (LidarOdometry.cpp:527 sets 0.015)
   int dogleg_type = 0;  // 0 TRADITIONAL_DOGLEG, 1 SUBSPACE_DOGLEG
   bool use_nonmonotonic_steps = false;
   int max_consecutive_nonmonotonic_steps = 5;

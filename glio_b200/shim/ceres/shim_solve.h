@@ -169,6 +169,7 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
   }
   glio::SolverOptions so;
   so.max_num_iterations = options.max_num_iterations;
+  so.max_solver_time_in_seconds = options.max_solver_time_in_seconds;
   so.dogleg_type = options.dogleg_type == SUBSPACE_DOGLEG ? 1 : 0;
   so.use_nonmonotonic_steps = options.use_nonmonotonic_steps;
   so.max_consecutive_nonmonotonic_steps = options.max_consecutive_nonmonotonic_steps;
