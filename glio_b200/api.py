@@ -28,7 +28,7 @@ class Params(C.Structure):
     _fields_ = [("kd_max_radius", C.c_double), ("surf_dist_thres", C.c_double), ("lidar_const", C.c_double),
                 ("weight_min", C.c_double), ("huber_delta", C.c_double), ("q_lb", C.c_double * 4),
                 ("t_lb", C.c_double * 3), ("batch_max_radius", C.c_double), ("batch_dist_thres", C.c_double),
-                ("batch_score", C.c_double), ("cell_size", C.c_float), ("keep_debug", C.c_int32)]
+                ("batch_score", C.c_double), ("cell_size", C.c_float), ("keep_debug", C.c_int32), ("unit_score", C.c_int32)]
 
 
 def lib():

@@ -289,6 +289,7 @@ EvalParams eval_params(const glio_ctx* c) {
   for (int k = 0; k < 3; ++k) ep.t_lb[k] = c->prm.t_lb[k];
   ep.lidar_const = c->prm.lidar_const;
   ep.huber_delta = c->prm.huber_delta;
+  ep.unit_score = c->prm.unit_score != 0 ? 1 : 0;
   return ep;
 }
 
@@ -368,7 +369,7 @@ void glio_default_params(glio_params* p) {
   p->kd_max_radius = 1.5; p->surf_dist_thres = 0.18; p->lidar_const = 7.5; p->weight_min = 0.3; p->huber_delta = 1.0;
   p->q_lb[0] = 1.0; p->t_lb[2] = 0.28;          // GLIO/config/config_urban_hk.yaml:90-97
   p->batch_max_radius = 1.5; p->batch_dist_thres = 0.18; p->batch_score = 2.5;
-  p->cell_size = 0.f; p->keep_debug = 0;
+  p->cell_size = 0.f; p->keep_debug = 0; p->unit_score = 0;
 }
 
 int glio_create(int device, const glio_params* params, glio_ctx** out) {

@@ -203,6 +203,7 @@ struct EvalParams {
   double q_lb[4], t_lb[3];
   double lidar_const;
   double huber_delta;
+  int unit_score;       // 1: score = lidar_const for every match (front-end factor), 0: lidar_const * weight
 };
 constexpr int GLIO_NACC = 28;        // 21 upper-triangular H + 6 g + 1 cost
 constexpr int EV_MAXW = 64;          // poses are passed in the kernel parameters up to this many keyframes

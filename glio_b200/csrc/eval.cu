@@ -63,7 +63,7 @@ struct KfFrame {           // per keyframe, prepared in shared memory
 template <bool WANT_JAC, int JAC_KIND>
 __device__ __forceinline__ void unary_accumulate(const float4 c4, const float4 n4, const double (&M)[9], const double (&t)[3],
                                                  const KfFrame& F, const EvalParams& ep, double (&acc)[NACC]) {
-  const double s = ep.lidar_const * (double)c4.w;            // Estimator.cpp:3692 score = lidar_const*weight
+  const double s = ep.unit_score ? ep.lidar_const : ep.lidar_const * (double)c4.w;   // Estimator.cpp:3692 score = lidar_const*weight; front end: no score
   const double dx = (double)c4.x - ep.t_lb[0], dy = (double)c4.y - ep.t_lb[1], dz = (double)c4.z - ep.t_lb[2];
   double a[3]; mat_vec3(M, dx, dy, dz, a);                   // a = R(q) q_lb^-1 (cp - t_lb)
   const double nx = (double)n4.x, ny = (double)n4.y, nz = (double)n4.z;
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) k_unary_residuals(const float4* __restric
   if (i >= n) return;
   const float4 c4 = cpw[i];
   const float4 n4 = nsd[i];
-  const double s = ep.lidar_const * (double)c4.w;
+  const double s = ep.unit_score ? ep.lidar_const : ep.lidar_const * (double)c4.w;
   const double dx = (double)c4.x - ep.t_lb[0], dy = (double)c4.y - ep.t_lb[1], dz = (double)c4.z - ep.t_lb[2];
   double a[3]; mat_vec3(F.M, dx, dy, dz, a);
   const double nx = (double)n4.x, ny = (double)n4.y, nz = (double)n4.z;

@@ -88,8 +88,9 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
       bool ext_ok = true;
       for (int k = 0; k < 4; ++k) ext_ok = ext_ok && d.q_lb[k] == gp.q_lb[k];
       for (int k = 0; k < 3; ++k) ext_ok = ext_ok && d.t_lb[k] == gp.t_lb[k];
-      const double w = d.score / gp.lidar_const;
-      const bool repr = is_f32(w) && gp.lidar_const * (double)(float)w == d.score && is_f32(d.cp[0]) && is_f32(d.cp[1]) && is_f32(d.cp[2]) &&
+      // unit_score contexts evaluate every match with score = lidar_const (front-end factor): only blocks with exactly that score qualify
+      const double w = gp.unit_score ? 1.0 : d.score / gp.lidar_const;
+      const bool repr = (gp.unit_score ? d.score == gp.lidar_const : (is_f32(w) && gp.lidar_const * (double)(float)w == d.score)) && is_f32(d.cp[0]) && is_f32(d.cp[1]) && is_f32(d.cp[2]) &&
                         is_f32(d.n[0]) && is_f32(d.n[1]) && is_f32(d.n[2]) && is_f32(d.d);
       if (loss_ok && blocks_ok && ext_ok && repr) {
         auto key = std::make_pair(t, q);

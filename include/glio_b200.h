@@ -58,6 +58,10 @@ typedef struct {
   double batch_score;      /* 2.5 hard-coded (Estimator.cpp:3798) */
   float cell_size;         /* uniform-grid cell edge in metres; 0 = choose from point density */
   int32_t keep_debug;      /* 1: keep idx5/sqd5/plane/pm per query for glio_get_assoc_debug (parity tests) */
+  int32_t unit_score;      /* 0: residual score = lidar_const*weight (LidarPlaneNormFactor, Estimator.cpp:3690);
+                            * 1: score = lidar_const for every match - with lidar_const = 1, identity extrinsic, kd_max_radius 1.0,
+                            *    surf_dist_thres 0.06, weight_min 0.4, huber_delta 0.1 this is the front end's scan matcher
+                            *    (LidarOdometry.cpp:343-404, :499-521; LidarPlaneNormIncreFactor, LidarKeyframeFactor.h:222-257) */
 } glio_params;
 
 void glio_default_params(glio_params* p);

@@ -74,3 +74,43 @@ def test_window_solve_matches_oracle(oracle, use_sb, n_sel, fuse):
         assert np.max(np.abs(rb["poses"] - rg["poses"])) <= 1e-12
     finally:
         ctx.close()
+
+
+def test_front_end_scan_matcher_settings(oracle):
+    """the front end's scan-to-map matcher (LidarOdometry.cpp:343-404, :474-540) is the same kernel recipe with
+    other constants: squared radius 1.0, plane threshold 0.06, weight gate 0.4, Huber 0.1, no extrinsic, residual
+    (w n).(q p + t) + w d without the lidar_const*weight score (LidarPlaneNormIncreFactor) -> unit_score = 1, lidar_const = 1."""
+    from glio_b200 import api
+    P = synth.window_problem(W=1, Q=4000, M=60000, seed=synth.SEED0 + 9)
+    ident_q, zero_t = [1.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0]
+    ctx = api.Context(0, keep_debug=1, kd_max_radius=1.0, surf_dist_thres=0.06, weight_min=0.4, lidar_const=1.0, huber_delta=0.1,
+                      q_lb=ident_q, t_lb=zero_t, unit_score=1)
+    try:
+        ctx.set_map(P["map_xyz"])
+        pose = P["poses_init"][0].copy()
+        # the scan was generated in the lidar frame of the synthetic extrinsic; with an identity extrinsic the lidar pose IS the state
+        t2, q2 = synth.lidar_pose_in_world(pose[:3], pose[3:7])
+        state = np.concatenate([t2, q2])[None, :]
+        ctx.window_set_scans([P["scans"][0]])
+        nm = ctx.window_associate(state)
+        prm = oracle.default_params(); prm.kd_max_radius = 1.0; prm.surf_dist_thres = 0.06; prm.weight_min = 0.4; prm.lidar_const = 1.0
+        o = oracle.assoc_scan_to_map(P["map_xyz"], P["scans"][0], t2, q2, prm=prm)
+        d = ctx.get_assoc_debug(0, 4000)
+        assert np.array_equal(d["status"], o["status"]) and nm[0] == o["nvalid"] > 300
+        assert (o["status"] == oracle.GO_FAIL_WEIGHT).any() or (o["status"] == oracle.GO_FAIL_PLANE).any()      # the tighter gates bite
+        v = o["status"] == oracle.GO_VALID
+        kf = np.zeros(int(v.sum()), np.int32); ones = np.ones(int(v.sum()))
+        oe = oracle.eval_unary(state, ident_q, zero_t, kf, P["scans"][0][v], o["nsd"][v], ones, huber_delta=0.1, mode=0)
+        ge = ctx.eval_unary(state)
+        assert np.max(np.abs(ge["H"][0] - oe["H"])) <= 1e-11 * np.max(np.abs(oe["H"]))
+        assert np.max(np.abs(ge["g"][0] - oe["g"])) <= 1e-11 * np.max(np.abs(oe["g"])) and abs(ge["cost"][0] - oe["cost_total"]) <= 1e-11 * oe["cost_total"]
+        # one Ceres solve of the front end's loop (6-dof, LiDAR residuals only)
+        prob = oracle.WindowProblem(state, None, ident_q, zero_t, huber_delta=0.1)
+        prob.add_unary(kf, P["scans"][0][v], o["nsd"][v], ones)
+        ro = prob.solve(oracle.solver_options(), mode=0)
+        rg = ctx.window_solve(state, None, None, api.default_solver_options())
+        assert rg["summary"].num_iterations == ro["summary"].num_iterations >= 2
+        for a, b in zip(rg["steps"], ro["steps"]):
+            assert np.max(np.abs(a[:3] - b[:3])) <= 1e-6 and np.max(np.abs(a[3:6] - b[3:6])) <= 1e-8
+    finally:
+        ctx.close()
