@@ -161,6 +161,21 @@ int main() {
     char name[64]; snprintf(name, sizeof(name), "Powell_%d%d%d%d", (int)cases[c][0], (int)cases[c][1], (int)cases[c][2], (int)cases[c][3]);
     report(name, ok, std::vector<double>(out, out + 4));
   }
+  {  // Solver::Options::max_solver_time_in_seconds (trust_region_minimizer.cc:327-329, :605-619): a zero budget stops the
+     // solve before the first step with NO_CONVERGENCE, as the reference's front end relies on (LidarOdometry.cpp:527)
+    std::vector<glio::ParamBlock> blocks{glio::ParamBlock{0, 6, 0, 6, false, nullptr}};
+    glio::SolverOptions o; o.max_solver_time_in_seconds = 0.0;
+    glio::TrustRegionDogleg solver(blocks, o);
+    glio::EvalFn eval = [&](const double* x, bool want_jac, double* cost, BandMat* H, double* g) -> bool {
+      double c = 0; for (int i = 0; i < 6; ++i) c += 0.5 * (x[i] - 1.0) * (x[i] - 1.0);
+      *cost = c;
+      if (want_jac) { H->reset(6, 5); for (int i = 0; i < 6; ++i) { H->at(i, i) = 1.0; g[i] = x[i] - 1.0; } }
+      return true;
+    };
+    std::vector<double> x0(6, 0.0); glio::SolverSummary S;
+    solver.solve(x0.data(), eval, &S);
+    report("MaxSolverTimeReached", S.termination == glio::TERM_NO_CONVERGENCE && S.message.find("Maximum solver time reached") == 0 && S.steps.empty() && x0[0] == 0.0, x0);
+  }
   poly_case("Poly_LinearPositive", {42.42}, 1e-13); poly_case("Poly_LinearNegative", {-42.42}, 1e-13);
   poly_case("Poly_QuadraticPositive", {1.0, 42.42}, 1e-13); poly_case("Poly_QuadraticOneNegative", {-42.42, 1.0}, 1e-13);
   poly_case("Poly_QuadraticTwoNegative", {-42.42, -1.0}, 1e-13); poly_case("Poly_QuadraticClose", {42.42, 42.43}, 1e-9);
