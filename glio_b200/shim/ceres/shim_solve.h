@@ -321,14 +321,15 @@ inline bool Problem::Evaluate(const EvaluateOptions& eo, double* cost, std::vect
   double ct = 0;
   if (residuals) residuals->clear();
   std::map<double*, int> toff; int nt = 0;
-  for (double* u : order_) { const Block& b = blocks_.at(u); if (b.constant) continue; toff[u] = nt; nt += b.param ? b.param->LocalSize() : b.size; }
+  // every parameter block of the problem owns its columns, constant ones with a zero gradient (Ceres: problem_test.cc:1363-1394)
+  for (double* u : order_) { const Block& b = blocks_.at(u); toff[u] = nt; nt += b.param ? b.param->LocalSize() : b.size; }
   if (gradient) gradient->assign(nt, 0.0);
   for (auto& rb : residual_blocks_) {
     const int nb = (int)rb->params.size(), nr = rb->cost->num_residuals();
     const std::vector<int32_t>& sz = rb->cost->parameter_block_sizes();
     std::vector<const double*> pp(rb->params.begin(), rb->params.end());
     std::vector<std::vector<double>> J(nb); std::vector<double*> jj(nb, nullptr); std::vector<double> r(nr);
-    if (gradient) for (int b = 0; b < nb; ++b) if (toff.count(rb->params[b])) { J[b].assign((size_t)nr * sz[b], 0.0); jj[b] = J[b].data(); }
+    if (gradient) for (int b = 0; b < nb; ++b) if (toff.count(rb->params[b]) && !blocks_.at(rb->params[b]).constant) { J[b].assign((size_t)nr * sz[b], 0.0); jj[b] = J[b].data(); }
     if (!rb->cost->Evaluate(pp.data(), r.data(), gradient ? jj.data() : nullptr)) return false;
     double sq = 0; for (double v : r) sq += v * v;
     double rho[3] = {sq, 1.0, 0.0};

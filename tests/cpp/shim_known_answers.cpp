@@ -4,6 +4,7 @@
 //   corrector_test.cc:58-147            Corrector scalar cases (shim_internal::Corr)
 //   local_parameterization_test.cc:232-352  QuaternionParameterization Plus / ComputeJacobian: zero, near-zero, away from zero
 //   rotation_test.cc (quaternion product / rotate point identities used by the factors)
+//   problem_test.cc:1064-1249, :1363-1394  Problem::Evaluate known answers (cost 7607, residuals, gradient; constant block)
 //   jet_test.cc style checks: every Jet function the reference's functors use, derivative vs symmetric differences
 // Prints "name ok|FAIL value" lines; tests/test_shim_known_answers.py asserts on them.
 #include <cmath>
@@ -54,6 +55,47 @@ template <typename F> static bool jet_fn(F f, double x, std::function<double(dou
   const double h = 1e-6 * std::max(1.0, std::fabs(x));
   const double fd = (g(x + h) - g(x - h)) / (2 * h);
   return std::fabs(r.a - g(x)) <= 1e-14 * std::max(1.0, std::fabs(g(x))) && std::fabs(r.v[0] - fd) <= 1e-7 * std::max(1.0, std::fabs(fd));
+}
+
+// problem_test.cc:1064-1099: residual_i = i - sum_j (j+1) * p_j[i]^2, jacobian_j = diag(-2 (j+1) p_j)
+template <int kNumResiduals, int kNumParameterBlocks>
+class QuadraticCostFunction : public ceres::CostFunction {
+ public:
+  QuadraticCostFunction() {
+    set_num_residuals(kNumResiduals);
+    for (int i = 0; i < kNumParameterBlocks; ++i) mutable_parameter_block_sizes()->push_back(kNumResiduals);
+  }
+  bool Evaluate(double const* const* parameters, double* residuals, double** jacobians) const final {
+    for (int i = 0; i < kNumResiduals; ++i) {
+      residuals[i] = i;
+      for (int j = 0; j < kNumParameterBlocks; ++j) residuals[i] -= (j + 1.0) * parameters[j][i] * parameters[j][i];
+    }
+    if (jacobians == NULL) return true;
+    for (int j = 0; j < kNumParameterBlocks; ++j)
+      if (jacobians[j] != NULL)
+        for (int r = 0; r < kNumResiduals; ++r) for (int c = 0; c < kNumResiduals; ++c) jacobians[j][r * kNumResiduals + c] = r == c ? -2.0 * (j + 1.0) * parameters[j][r] : 0.0;
+    return true;
+  }
+};
+
+// problem_test.cc:1110-1146 fixture + :1221-1249 / :1363-1394 expectations (cost, residuals, gradient)
+static void problem_evaluate_tests() {
+  for (int constant_y = 0; constant_y < 2; ++constant_y) {
+    double parameters[6]; for (int i = 0; i < 6; ++i) parameters[i] = i + 1.0;
+    ceres::Problem problem;
+    ceres::CostFunction* cost_function = new QuadraticCostFunction<2, 2>;
+    problem.AddResidualBlock(cost_function, NULL, parameters, parameters + 2);        // f(x, y)
+    problem.AddResidualBlock(cost_function, NULL, parameters + 2, parameters + 4);    // g(y, z)
+    problem.AddResidualBlock(cost_function, NULL, parameters + 4, parameters);        // h(z, x)
+    if (constant_y) problem.SetParameterBlockConstant(parameters + 2);
+    const double exp_res[6] = {-19.0, -35.0, -59.0, -87.0, -27.0, -43.0};
+    const double exp_grad[2][6] = {{146.0, 484.0, 582.0, 1256.0, 1450.0, 2604.0}, {146.0, 484.0, 0.0, 0.0, 1450.0, 2604.0}};
+    double cost = 0; std::vector<double> residuals, gradient;
+    bool ok = problem.Evaluate(ceres::Problem::EvaluateOptions(), &cost, &residuals, &gradient, NULL);
+    ok = ok && cost == 7607.0 && residuals.size() == 6 && gradient.size() == 6;
+    for (int i = 0; ok && i < 6; ++i) ok = residuals[i] == exp_res[i] && gradient[i] == exp_grad[constant_y][i];
+    report(constant_y ? "ProblemEvaluate_ConstantParameterBlock" : "ProblemEvaluate_MultipleParameterAndResidualBlocks", ok, cost);
+  }
 }
 
 int main() {
@@ -146,5 +188,6 @@ int main() {
     report("Jet_atan2", jet_fn([](J a) { return atan2(a, J(0.8) + a * 0.5); }, 0.6, [](double x) { return std::atan2(x, 0.8 + 0.5 * x); }));
     report("Jet_div", jet_fn([](J a) { return (J(1.0) + a * a) / (a + 2.0) - 3.0 / a; }, 0.9, [](double x) { return (1 + x * x) / (x + 2) - 3.0 / x; }));
   }
+  problem_evaluate_tests();
   return n_fail ? 1 : 0;
 }
