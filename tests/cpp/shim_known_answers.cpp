@@ -5,6 +5,7 @@
 //   local_parameterization_test.cc:232-352  QuaternionParameterization Plus / ComputeJacobian: zero, near-zero, away from zero
 //   rotation_test.cc (quaternion product / rotate point identities used by the factors)
 //   problem_test.cc:1064-1249, :1363-1394  Problem::Evaluate known answers (cost 7607, residuals, gradient; constant block)
+//   autodiff_cost_function_test.cc:42-143   AutoDiffCostFunction residuals / Jacobians (bilinear, ten parameter blocks)
 //   jet_test.cc style checks: every Jet function the reference's functors use, derivative vs symmetric differences
 // Prints "name ok|FAIL value" lines; tests/test_shim_known_answers.py asserts on them.
 #include <cmath>
@@ -95,6 +96,36 @@ static void problem_evaluate_tests() {
     ok = ok && cost == 7607.0 && residuals.size() == 6 && gradient.size() == 6;
     for (int i = 0; ok && i < 6; ++i) ok = residuals[i] == exp_res[i] && gradient[i] == exp_grad[constant_y][i];
     report(constant_y ? "ProblemEvaluate_ConstantParameterBlock" : "ProblemEvaluate_MultipleParameterAndResidualBlocks", ok, cost);
+  }
+}
+
+// autodiff_cost_function_test.cc:42-143
+struct BinaryScalarCost {
+  explicit BinaryScalarCost(double a) : a_(a) {}
+  template <typename T> bool operator()(const T* const x, const T* const y, T* cost) const { cost[0] = x[0] * y[0] + x[1] * y[1] - T(a_); return true; }
+  double a_;
+};
+struct TenParameterCost {
+  template <typename T> bool operator()(const T* const x0, const T* const x1, const T* const x2, const T* const x3, const T* const x4, const T* const x5,
+                                        const T* const x6, const T* const x7, const T* const x8, const T* const x9, T* cost) const {
+    cost[0] = *x0 + *x1 + *x2 + *x3 + *x4 + *x5 + *x6 + *x7 + *x8 + *x9; return true;
+  }
+};
+static void autodiff_tests() {
+  {
+    ceres::AutoDiffCostFunction<BinaryScalarCost, 1, 2, 2> cf(new BinaryScalarCost(1.0));
+    double x[2] = {1, 2}, y[2] = {3, 4}; const double* params[2] = {x, y};
+    double jx[2], jy[2]; double* jac[2] = {jx, jy}; double r = 0, r2 = 0;
+    bool ok = cf.Evaluate(params, &r, nullptr) && r == 10.0 && cf.Evaluate(params, &r2, jac) && r2 == 10.0 && jx[0] == 3 && jx[1] == 4 && jy[0] == 1 && jy[1] == 2;
+    report("AutoDiff_BilinearDifferentiationTest", ok, r);
+  }
+  {
+    ceres::AutoDiffCostFunction<TenParameterCost, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1> cf(new TenParameterCost);
+    double p[10], j[10]; const double* params[10]; double* jac[10];
+    for (int i = 0; i < 10; ++i) { p[i] = i; params[i] = &p[i]; jac[i] = &j[i]; }
+    double r = 0; bool ok = cf.Evaluate(params, &r, nullptr) && r == 45.0 && cf.Evaluate(params, &r, jac) && r == 45.0;
+    for (int i = 0; ok && i < 10; ++i) ok = j[i] == 1.0;
+    report("AutoDiff_ManyParameterAutodiffInstantiates", ok, r);
   }
 }
 
@@ -189,5 +220,6 @@ int main() {
     report("Jet_div", jet_fn([](J a) { return (J(1.0) + a * a) / (a + 2.0) - 3.0 / a; }, 0.9, [](double x) { return (1 + x * x) / (x + 2) - 3.0 / x; }));
   }
   problem_evaluate_tests();
+  autodiff_tests();
   return n_fail ? 1 : 0;
 }

@@ -13,6 +13,6 @@ def test_shim_against_ceres_known_answers(tmp_path):
                            "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lcudart"])
     p = subprocess.run([exe], text=True, capture_output=True)
     lines = p.stdout.splitlines()
-    assert len(lines) == 36, p.stdout + p.stderr
+    assert len(lines) == 38, p.stdout + p.stderr
     bad = [l for l in lines if l.split()[1] != "ok"]
     assert not bad and p.returncode == 0, bad
