@@ -3,6 +3,7 @@
 
 #include <chrono>
 #include <complex>
+#include <cstdlib>
 
 namespace glio {
 namespace detail {
@@ -61,7 +62,7 @@ bool real_roots_deg4(const double* poly5, std::vector<double>* roots) {
   return true;
 }
 
-bool cholesky_solve(BandMat& A, const double* b, double* x) {
+bool cholesky_solve_scalar(BandMat& A, const double* b, double* x) {
   const int n = A.n, hb = A.hb, w = hb + 1;
   double* a = A.a.data();
   // right-looking band Cholesky: after column j is scaled, the trailing rows inside the band get a rank-1 update.
@@ -101,6 +102,15 @@ bool cholesky_solve(BandMat& A, const double* b, double* x) {
   }
   for (int i = 0; i < n; ++i) if (!std::isfinite(x[i])) return false;
   return true;
+}
+
+// dispatcher: the AVX2/FMA panel version (band_chol_avx2.cpp) when the CPU has it, else the portable one
+bool cholesky_solve(BandMat& A, const double* b, double* x) {
+#if defined(__x86_64__)
+  static const bool fast = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma") && std::getenv("GLIO_NO_AVX2") == nullptr;
+  if (fast && A.hb >= 4 && A.n >= 8) return cholesky_solve_avx2(A, b, x);
+#endif
+  return cholesky_solve_scalar(A, b, x);
 }
 
 }  // namespace detail

@@ -104,6 +104,10 @@ inline void quat_plus(const double* x, const double* d, double* o) {
 
 // In-place band Cholesky A = L L^T (lower band storage) and solve L L^T x = b (solver.cpp, right-looking).  Returns false if a pivot is not positive / finite (Ceres: LINEAR_SOLVER_FAILURE -> mu escalation).
 bool cholesky_solve(BandMat& A, const double* b, double* x);
+bool cholesky_solve_scalar(BandMat& A, const double* b, double* x);   // portable path
+#if defined(__x86_64__)
+bool cholesky_solve_avx2(BandMat& A, const double* b, double* x);     // band_chol_avx2.cpp; call only when the CPU has AVX2 + FMA
+#endif
 
 // real roots of a polynomial of degree <= 4 (highest power first), for the subspace dogleg
 // (dogleg_strategy.cc:421-446 uses FindPolynomialRoots; here: Durand-Kerner + Newton polish in long double).
