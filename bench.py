@@ -81,6 +81,9 @@ class ClockSampler:
         except Exception:
             pass
 
+    def reset(self):
+        self.samples = []; self.reasons = set()
+
     def result(self):
         return dict(sm_mhz=float(np.median(self.samples)) if self.samples else None, sm_max_mhz=self.max_mhz,
                     reasons=sorted(self.reasons), samples=len(self.samples), how="NVML, read inside the timed region at step boundaries")
@@ -203,9 +206,15 @@ def run_glio(args, rank, world, local_rank):
             dist.barrier()
         return iters, ms, wall
 
+    # NVML is initialised and queried during the warm-up steps: the first query of a process can stall the GPU work queue for
+    # tens of milliseconds on some boxes (measured: a fixed ~85 ms once per process), which must not land in the timed region.
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         one_step(dmap, dscans)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler is not None:
+            sampler.sample()
+    if sampler is not None:
+        sampler.reset()
     # (A) the reported value: K steps, inputs resident in HBM, no per-kernel instrumentation
     l0 = ctx.launch_count
     iters, ms, wall = timed_run(dmap, dscans, args.steps, sampler)
