@@ -45,7 +45,7 @@ def host_factor_spec(P, rng):
 
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region through NVML, from the timing thread itself at step
-    boundaries (every few steps; one read costs tens of microseconds and is inside the timed region).  Polling from
+    boundaries (about five reads per run; one read stalls the launch queue for up to ~0.5 ms and is inside the timed region).  Polling from
     outside — an `nvidia-smi -lms` subprocess or a concurrent NVML thread — was measured to stall this workload's
     many short launches by milliseconds per step."""
 
@@ -184,7 +184,7 @@ def run_glio(args, rank, world, local_rank):
 
     def timed_run(m, scans, nsteps, sampler=None):
         iters = 0
-        every = max(1, nsteps // 8)
+        every = max(1, nsteps // 4)                 # ~5 NVML reads per run: one read costs ~0.5 ms of stalled launches on this box
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -196,7 +196,7 @@ def run_glio(args, rank, world, local_rank):
                 flush.fill_(1)                      # L2 flush between steps (256 MB > 126 MB L2), inside the timed region
             it, _r = one_step(m, scans)
             iters += it
-            if sampler is not None and si % every == 0:
+            if sampler is not None and (si % every == 0 or si == nsteps - 1):
                 sampler.sample()
         e1.record(st)
         torch.cuda.synchronize()
