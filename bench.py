@@ -184,7 +184,7 @@ def run_glio(args, rank, world, local_rank):
 
     def timed_run(m, scans, nsteps, sampler=None):
         iters = 0
-        every = max(1, nsteps // 4)                 # ~5 NVML reads per run: one read costs ~0.5 ms of stalled launches on this box
+        every = max(1, (nsteps + 3) // 4)              # ~5 NVML reads per run: one read costs ~0.5 ms of stalled launches on this box
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
