@@ -131,7 +131,7 @@ class Context:
         self._lib.glio_lidar_pose(C.byref(self.params), _ptr(pb), _ptr(t2), _ptr(q2))
         return t2, q2
 
-    KERNELS = ["k_knn_search", "k_knn_deferred", "k_knn_thread", "k_knn_box", "k_plane_fit", "k_plane_fit_pair", "k_eval_unary", "k_eval_unary_cost", "k_transform_hist", "k_order_scatter",
+    KERNELS = ["k_knn_tile", "k_knn_team", "k_make_pairs", "k_knn_search", "k_knn_deferred", "k_knn_thread", "k_knn_box", "k_plane_fit", "k_plane_fit_pair", "k_eval_unary", "k_eval_unary_cost", "k_transform_hist", "k_order_scatter",
                "k_compact", "k_flags", "k_cell_hist", "k_cell_scatter", "k_load_bounds", "k_scan_block", "k_scan_add",
                "k_eval_binary", "k_eval_binary_cost", "k_bin_assemble",
                "k_lm_transform", "k_vox_hist", "k_vox_scatter", "k_vox_sort", "k_vox_flags", "k_vox_centroid", "k_init_bounds"]
@@ -271,7 +271,7 @@ class SolverOptions(C.Structure):
                 ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
                 ("max_num_consecutive_invalid_steps", C.c_int32), ("jacobi_scaling", C.c_int32),
                 ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
-                ("fuse_candidate_jacobian", C.c_int32), ("reserved", C.c_int32)]
+                ("fuse_candidate_jacobian", C.c_int32), ("trust_region_strategy", C.c_int32)]
 
 
 class Iteration(C.Structure):

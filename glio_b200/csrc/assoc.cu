@@ -13,6 +13,7 @@
 // intrinsics of devmath.cuh: kNN indices and the valid mask must be bit-exact w.r.t. the no-FMA reference.
 #include "common.cuh"
 #include "devmath.cuh"
+#include "knn_common.cuh"
 
 namespace glio {
 
@@ -56,37 +57,6 @@ __global__ void __launch_bounds__(256) k_order_scatter(GridDesc grid, int64_t Qt
   order[pos] = (uint32_t)g;
 }
 
-// ---- top-5 by (distance, index) -------------------------------------------------------------------
-// One 64-bit key per neighbour: (bits of the non-negative float distance) << 32 | index.  Unsigned key order ==
-// lexicographic (distance, index) order, so ties are broken by index exactly like a stable sort by (distance, index).
-struct Top5 {
-  unsigned long long k0, k1, k2, k3, k4;
-};
-__device__ __forceinline__ unsigned long long make_key(float d, int id) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)id; }
-__device__ __forceinline__ float key_dist(unsigned long long k) { return __uint_as_float((unsigned int)(k >> 32)); }
-__device__ __forceinline__ int key_idx(unsigned long long k) { return (int)(unsigned int)(k & 0xffffffffull); }
-constexpr unsigned long long KEY_EMPTY = 0x7f8000007fffffffull;   // (+inf, INT_MAX)
-__device__ __forceinline__ void top5_init(Top5& t) { t.k0 = t.k1 = t.k2 = t.k3 = t.k4 = KEY_EMPTY; }
-// compare-exchange of two keys: one 64-bit compare + select for the smaller key, the larger one by XOR (the plain
-// two-select form made ptxas emit a second, mirrored compare: 8 instead of 6 instructions per exchange in the hottest
-// block of K1a)
-__device__ __forceinline__ void key_cswap(unsigned long long& a, unsigned long long& b) {
-  const unsigned long long lo = a < b ? a : b;
-  b = a ^ b ^ lo;
-  a = lo;
-}
-#define GLIO_KSWAP(A, B) key_cswap((A), (B));
-__device__ __forceinline__ void top5_push(Top5& t, float d, int id) {
-  const unsigned long long k = make_key(d, id);
-  if (k < t.k4) {
-    t.k4 = k;
-    GLIO_KSWAP(t.k3, t.k4)
-    GLIO_KSWAP(t.k2, t.k3)
-    GLIO_KSWAP(t.k1, t.k2)
-    GLIO_KSWAP(t.k0, t.k1)
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // K1a (warp-cooperative variant, GLIO_KNN_MODE=0; not the default - see DESIGN.md section 4 for the measurements).
 // Queries arrive sorted by grid cell, so the 32 queries of a warp sit in a short run of x-adjacent cells of one
@@ -97,34 +67,8 @@ __device__ __forceinline__ void top5_push(Top5& t, float d, int id) {
 // box covers the gate radius (anything unseen then fails the radius gate anyway).
 // Intermediate results are written in sorted order, structure-of-arrays: coalesced here and in K1b.
 // ---------------------------------------------------------------------------------------------------
-// ---- packed fp32x2 arithmetic (Blackwell FADD2/FMUL2/FFMA2) for the candidate PRE-FILTER only.
-// ptxas contracts packed mul+add into FFMA2 even for .rn operands and under -fmad=false, so packed results may
-// differ from the reference's unfused ((dx*dx)+dy*dy)+dz*dz by a few ulps.  They are therefore used only to reject
-// candidates that are clearly farther than the current 5th distance (with a 1e-6 relative margin); every candidate
-// that might matter is re-evaluated with the exact scalar l2_simple() before it can enter the top-5.
-typedef unsigned long long f32x2_t;
-__device__ __forceinline__ f32x2_t pack2(float a, float b) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void unpack2(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-
 constexpr int KNN_WARPS = 4;
 constexpr int KNN_SPAN_MAX = 12;
-
-struct SearchArgs {
-  GridDesc grid;
-  int64_t Qt;
-  const float4* pm;
-  const uint32_t* order;
-  float gate_sq;
-  int32_t* knn_idx;     // [5][Qt] sorted order
-  float* knn_sqd;       // [5][Qt] sorted order
-  unsigned long long* n_fallback;   // statistics: queries deferred to the single-query pass
-  int tile_rings;                   // rings the tile pass may scan before it defers a query (1)
-  uint32_t* deferred;               // sorted positions of deferred queries
-  unsigned int* n_deferred;
-};
 
 __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
   __shared__ __align__(16) float sx[KNN_WARPS][32], sy[KNN_WARPS][32], sz[KNN_WARPS][32];
@@ -315,13 +259,6 @@ __device__ __forceinline__ bool thread_rings(const GridDesc& g, float qx, float 
     if (bs > 0.f && key_dist(t.k4) <= bs * bs) return true;
   }
   return r_hi >= rmax;
-}
-
-__device__ __forceinline__ void store_top5(const SearchArgs& a, int64_t p, const Top5& t) {
-  a.knn_idx[0 * a.Qt + p] = key_idx(t.k0); a.knn_idx[1 * a.Qt + p] = key_idx(t.k1); a.knn_idx[2 * a.Qt + p] = key_idx(t.k2);
-  a.knn_idx[3 * a.Qt + p] = key_idx(t.k3); a.knn_idx[4 * a.Qt + p] = key_idx(t.k4);
-  a.knn_sqd[0 * a.Qt + p] = key_dist(t.k0); a.knn_sqd[1 * a.Qt + p] = key_dist(t.k1); a.knn_sqd[2 * a.Qt + p] = key_dist(t.k2);
-  a.knn_sqd[3 * a.Qt + p] = key_dist(t.k3); a.knn_sqd[4 * a.Qt + p] = key_dist(t.k4);
 }
 
 // K1a (ring growth, knn_mode 1): one query per thread, whole rings until the 5th distance is provably inside the box.
@@ -622,7 +559,9 @@ void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const Assoc
   sa.tile_rings = w.tile_rings; sa.deferred = w.deferred; sa.n_deferred = w.n_deferred;
   GLIO_CUDA_TRY(cudaMemsetAsync(w.n_deferred, 0, sizeof(unsigned int), st));
   const unsigned ns = (unsigned)((Qt + 32 * KNN_WARPS - 1) / (32 * KNN_WARPS));
-  if (w.knn_mode == 2 || w.knn_mode == 3) {
+  if (w.knn_mode == 4) {
+    knn_tile_run(sa, gb.pairs.p, st, lc);
+  } else if (w.knn_mode == 2 || w.knn_mode == 3) {
     lc.begin("k_knn_box", st);
     if (w.knn_mode == 3) k_knn_box<true><<<(unsigned)((Qt + 127) / 128), 128, 0, st>>>(sa);
     else k_knn_box<false><<<(unsigned)((Qt + 127) / 128), 128, 0, st>>>(sa);

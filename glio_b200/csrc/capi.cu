@@ -385,9 +385,10 @@ int glio_create(int device, const glio_params* params, glio_ctx** out) {
     c = new glio_ctx();
     c->device = device;
     if (params) c->prm = *params; else glio_default_params(&c->prm);
-    if (const char* e = getenv("GLIO_KNN_MODE")) { const int v = atoi(e); if (v >= 0 && v <= 3) c->knn_mode = v; }
+    if (const char* e = getenv("GLIO_KNN_MODE")) { const int v = atoi(e); if (v >= 0 && v <= 4) c->knn_mode = v; }
     if (const char* e = getenv("GLIO_TILE_RINGS")) { const int v = atoi(e); if (v >= 1 && v < 64) c->tile_rings = v; }
     if (const char* e = getenv("GLIO_PTS_PER_CELL")) { const float v = (float)atof(e); if (v > 0.1f && v < 1000.f) c->pts_per_cell = v; }
+    c->map.build_pairs = c->knn_mode == 4;
     GLIO_CUDA_TRY(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     GLIO_CUDA_TRY(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
     GLIO_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_scans, cudaEventDisableTiming));
@@ -789,6 +790,8 @@ static int window_solve_impl(glio_ctx* c, int W, double* poses, double* speed_bi
     so.max_num_consecutive_invalid_steps = o.max_num_consecutive_invalid_steps; so.jacobi_scaling = o.jacobi_scaling != 0;
     so.function_tolerance = o.function_tolerance; so.gradient_tolerance = o.gradient_tolerance; so.parameter_tolerance = o.parameter_tolerance;
     so.fuse_candidate_jacobian = o.fuse_candidate_jacobian != 0;
+    GLIO_REQUIRE(o.trust_region_strategy == 0 || o.trust_region_strategy == 1, GLIO_ERR_ARG, "trust_region_strategy must be 0 (DOGLEG) or 1 (LEVENBERG_MARQUARDT)");
+    so.trust_region_strategy = o.trust_region_strategy;
     TrustRegionDogleg solver(blocks, so);
     std::vector<double> x((size_t)W * na), pz((size_t)W * 7), sz((size_t)W * 9);
     for (int k = 0; k < W; ++k) {
@@ -947,6 +950,7 @@ int glio_batch_associate_pairs(glio_ctx* c, const int32_t* pairs_cur, const int3
       glio_ctx::Frame& fo = *c->frames[grp.first];
       if (!fo.grid_valid) {
         // world cloud of the searched frame (body pose applied directly to the stored points, quirk Q7) + its grid
+        fo.grid.build_pairs = c->knn_mode == 4;
         grid_build(fo.grid, fo.scan_ptr, fo.stride, fo.Q, fo.pose, fo.pose + 3, c->prm.cell_size, c->pts_per_cell, c->st, c->lc);
         fo.grid_valid = true;
       }
@@ -1215,6 +1219,8 @@ int glio_batch_solve(glio_ctx* c, int K, double* poses, double* speed_bias, glio
     so.max_num_consecutive_invalid_steps = o.max_num_consecutive_invalid_steps; so.jacobi_scaling = o.jacobi_scaling != 0;
     so.function_tolerance = o.function_tolerance; so.gradient_tolerance = o.gradient_tolerance; so.parameter_tolerance = o.parameter_tolerance;
     so.fuse_candidate_jacobian = o.fuse_candidate_jacobian != 0;
+    GLIO_REQUIRE(o.trust_region_strategy == 0 || o.trust_region_strategy == 1, GLIO_ERR_ARG, "trust_region_strategy must be 0 (DOGLEG) or 1 (LEVENBERG_MARQUARDT)");
+    so.trust_region_strategy = o.trust_region_strategy;
     TrustRegionDogleg solver(blocks, so);
     std::vector<double> x((size_t)K * na), pz((size_t)K * 7), sz((size_t)K * 9);
     for (int k = 0; k < K; ++k) {

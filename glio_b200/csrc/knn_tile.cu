@@ -1,0 +1,313 @@
+// knn_tile.cu — K1a, staged tile search (GLIO_KNN_MODE=4): exact 5-NN over the local map for
+// Estimator::findCorrespondingSurfFeatures (GLIO/src/Estimator.cpp:3643-3651, kd_tree->nearestKSearch(point, 5, ...)).
+//
+// Design (the north_star's "TMA / shared-memory staging of local-map tiles"):
+//   * queries arrive sorted by grid cell, so the 32 queries of a warp sit in a short run of x-adjacent cells of one (y,z)
+//     cell row.  The warp owns that TILE: the 3x3 cell rows around it, each row ONE contiguous, 32-byte aligned run of the
+//     pair-layout map (PairRec), are bulk-copied global -> shared by the copy engine (cp.async.bulk + mbarrier
+//     complete_tx; SASS UBLKCP), nine copies issued by nine lanes, no register staging, no per-thread gathers.
+//   * every lane then scans the SAME staged candidate list with uniform trip counts (broadcast LDS, no divergence):
+//       pass A  packed fp32x2 distances -> 8 interleaved running minima; the 5th smallest of them bounds the 5th
+//               neighbour distance from above (five distinct candidates are at least that close)
+//       pass B  packed distances again, candidates under the bound (x 1+1e-6: the packed arithmetic is fused) set a bit in
+//               a per-lane survivor mask (16 candidates per word, parked in shared memory; about 6-9 survive of ~190)
+//       flush   survivors re-evaluated with the exact FLANN L2_Simple<float> order and inserted in the (distance, index)
+//               top-5 -> the only place a result is decided, so indices and distances stay bit-exact
+//   * a lane whose 5th distance is provably inside the scanned box is final; the rest (sparse map, displaced query,
+//     oversized tile) go to the team pass with their 5th distance as the search radius.
+//   * team pass (k_knn_team): 8 lanes per deferred query split the cell rows of the sphere's bounding box (rows clipped
+//     to the circle the sphere cuts out of them), private top-5 each, merged with three shuffle rounds (half-cleaner +
+//     5-sorter per round).
+// Compiled with -fmad=false like assoc.cu; the packed helpers are pre-filters only (knn_common.cuh).
+#include "knn_common.cuh"
+
+namespace glio {
+
+constexpr int TK_WARPS = 4;          // warps (= tiles in flight) per CTA
+constexpr int TK_CAP_PAIRS = 256;    // staged pair records per tile (512 map points, 8 KB); larger tiles are deferred
+constexpr int TK_SPAN = 12;          // max x-extent (cells) of the queries sharing one tile
+constexpr float TK_MARGIN = 1.000002f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void cmpx(float& a, float& b) { const float lo = fminf(a, b), hi = fmaxf(a, b); a = lo; b = hi; }
+// 5th smallest of eight values (optimal 19-comparator network; unused outputs are dead code)
+__device__ __forceinline__ float fifth_of_8(float m0, float m1, float m2, float m3, float m4, float m5, float m6, float m7) {
+  cmpx(m0, m2); cmpx(m1, m3); cmpx(m4, m6); cmpx(m5, m7);
+  cmpx(m0, m4); cmpx(m1, m5); cmpx(m2, m6); cmpx(m3, m7);
+  cmpx(m0, m1); cmpx(m2, m3); cmpx(m4, m5); cmpx(m6, m7);
+  cmpx(m2, m4); cmpx(m3, m5);
+  cmpx(m1, m4); cmpx(m3, m6);
+  cmpx(m1, m2); cmpx(m3, m4); cmpx(m5, m6);
+  return m4;
+}
+
+__global__ void __launch_bounds__(32 * TK_WARPS) k_knn_tile(SearchArgs a, const PairRec* __restrict__ gpairs) {
+  __shared__ __align__(128) PairRec s_tile[TK_WARPS][TK_CAP_PAIRS + 8];
+  __shared__ uint16_t s_mask[TK_WARPS][(TK_CAP_PAIRS / 8 + 1) * 32];
+  __shared__ __align__(8) unsigned long long s_bar[TK_WARPS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t p = ((int64_t)blockIdx.x * TK_WARPS + wid) * 32 + lane;
+  const bool active = p < a.Qt;
+  const GridDesc& G = a.grid;
+  const float INF = __int_as_float(0x7f800000);
+  PairRec* tile = s_tile[wid];
+  uint16_t* mask = s_mask[wid] + lane;
+  unsigned long long* bar = &s_bar[wid];
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_proxy_async();
+  __syncwarp();
+
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (active) { const float4 q4 = a.pm[a.order[p]]; qx = q4.x; qy = q4.y; qz = q4.z; }
+  const int cx = cell_coord(qx, G.ox, G.inv_cell), cy = cell_coord(qy, G.oy, G.inv_cell), cz = cell_coord(qz, G.oz, G.inv_cell);
+  const float gate_r = sqrtf(a.gate_sq) + 2e-3f;
+  const int rmax = (int)ceilf(gate_r * G.inv_cell) + 1;
+  // far outside the grid: nothing within the gate radius
+  const bool far_out = cx < -rmax || cy < -rmax || cz < -rmax || cx >= G.nx + rmax || cy >= G.ny + rmax || cz >= G.nz + rmax;
+  Top5 t;
+  top5_init(t);
+  if (active && far_out) store_top5(a, p, t);
+  bool done = !active || far_out;
+  const f32x2_t qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
+  const float gate_cap = a.gate_sq * TK_MARGIN;
+  const int* __restrict__ cs = G.cell_start;
+  unsigned parity = 0;
+  unsigned long long n_def = 0;
+
+  for (;;) {
+    const unsigned pending = __ballot_sync(0xffffffffu, !done);
+    if (!pending) break;
+    const int leader = __ffs(pending) - 1;
+    const int lcx = __shfl_sync(0xffffffffu, cx, leader), lcy = __shfl_sync(0xffffffffu, cy, leader), lcz = __shfl_sync(0xffffffffu, cz, leader);
+    const bool part = !done && cy == lcy && cz == lcz && cx >= lcx && cx < lcx + TK_SPAN;
+    const int hix = __reduce_max_sync(0xffffffffu, part ? cx : lcx);
+    const int xa = lcx - 1, xb = hix + 1;                       // scanned cell range in x
+    const int x0 = max(xa, 0), x1 = min(xb, G.nx - 1);
+    // ---- the nine rows of the tile: bounds (lanes 0..8), offsets, staging
+    int s = 0, e = 0;
+    if (lane < 9) {
+      const int z = lcz + lane / 3 - 1, y = lcy + lane % 3 - 1;
+      if (z >= 0 && z < G.nz && y >= 0 && y < G.ny && x0 <= x1) {
+        const int row = (z * G.ny + y) * G.nx;
+        s = __ldg(&cs[row + x0]); e = __ldg(&cs[row + x1 + 1]);
+      }
+    }
+    const int ps = s >> 1;
+    const int np = e > s ? ((e + 1) >> 1) - ps : 0;
+    int off = np;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += v; }
+    const int total = __shfl_sync(0xffffffffu, off, 15);
+    off -= np;
+    const bool fits = total <= TK_CAP_PAIRS;
+    bool final_ok = false;
+    Top5 tt;
+    top5_init(tt);
+    if (fits && total > 0) {
+      fence_proxy_async();              // earlier generic-proxy accesses of this buffer (previous tile) before the async writes
+      __syncwarp();
+      if (lane == 0) mbar_expect_tx(bar, (unsigned)total * 32u);
+      __syncwarp();
+      if (np > 0) bulk_g2s(tile + off, gpairs + ps, (unsigned)np * 32u, bar);
+      mbar_wait(bar, parity);
+      parity ^= 1u;
+      // the pair run of a row may start / end with a half-record of the neighbouring cell: neutralise it
+      if (np > 0) {
+        if (s & 1) { tile[off].x0 = PAIR_FAR; tile[off].i0 = 0x7fffffff; }
+        if (e & 1) { tile[off + np - 1].x1 = PAIR_FAR; tile[off + np - 1].i1 = 0x7fffffff; }
+      }
+      const int npad = (total + 7) & ~7;
+      if (lane < npad - total) {
+        PairRec f; f.x0 = PAIR_FAR; f.x1 = PAIR_FAR; f.y0 = 0.f; f.y1 = 0.f; f.z0 = 0.f; f.z1 = 0.f; f.i0 = 0x7fffffff; f.i1 = 0x7fffffff;
+        tile[total + lane] = f;
+      }
+      __syncwarp();
+      if (part) {
+        const ulonglong2* T2 = reinterpret_cast<const ulonglong2*>(tile);
+        // ---- pass A: eight interleaved running minima of the packed distances
+        float m0 = INF, m1 = INF, m2 = INF, m3 = INF, m4 = INF, m5 = INF, m6 = INF, m7 = INF;
+#pragma unroll 1
+        for (int k = 0; k < npad; k += 4) {
+          float d[8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const ulonglong2 xy = T2[2 * (k + u)];
+            const unsigned long long zz = *reinterpret_cast<const unsigned long long*>(&T2[2 * (k + u) + 1]);
+            const f32x2_t dx = sub2(qx2, xy.x), dy = sub2(qy2, xy.y), dz = sub2(qz2, zz);
+            unpack2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), d[2 * u], d[2 * u + 1]);
+          }
+          m0 = fminf(m0, d[0]); m1 = fminf(m1, d[1]); m2 = fminf(m2, d[2]); m3 = fminf(m3, d[3]);
+          m4 = fminf(m4, d[4]); m5 = fminf(m5, d[5]); m6 = fminf(m6, d[6]); m7 = fminf(m7, d[7]);
+        }
+        // five distinct candidates lie within the 5th smallest minimum: an upper bound of the exact 5th distance once the
+        // fused packed arithmetic (<= 4e-7 relative from the unfused order) is covered by the margin; nothing beyond the
+        // radius gate can matter (Estimator.cpp:3651)
+        const float bound = fminf(fifth_of_8(m0, m1, m2, m3, m4, m5, m6, m7) * TK_MARGIN, gate_cap);
+        const float thr = bound * TK_MARGIN;
+        // ---- pass B: packed distances again; a 16-bit survivor mask per word of 8 pair records, parked in shared memory
+        const int nwords = npad >> 3;
+#pragma unroll 1
+        for (int w = 0; w < nwords; ++w) {
+          unsigned m = 0;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const ulonglong2 xy = T2[2 * (8 * w + u)];
+            const unsigned long long zz = *reinterpret_cast<const unsigned long long*>(&T2[2 * (8 * w + u) + 1]);
+            const f32x2_t dx = sub2(qx2, xy.x), dy = sub2(qy2, xy.y), dz = sub2(qz2, zz);
+            float d0, d1;
+            unpack2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), d0, d1);
+            if (d0 <= thr) m |= 1u << (2 * u);
+            if (d1 <= thr) m |= 2u << (2 * u);
+          }
+          mask[w * 32] = (uint16_t)m;
+        }
+        {
+          // ---- flush: survivors re-evaluated with the exact distance, exact (distance, index) order
+          const float* tf = reinterpret_cast<const float*>(tile);
+#pragma unroll 1
+          for (int w = 0; w < nwords; ++w) {
+            unsigned m = mask[w * 32];
+            while (m) {
+              const int j = __ffs(m) - 1;
+              m &= m - 1;
+              const float* rec = tf + (8 * w + (j >> 1)) * 8 + (j & 1);
+              const int id = __float_as_int(rec[6]);
+              top5_push(tt, l2_simple(qx, qy, qz, rec[0], rec[2], rec[4]), id);
+            }
+          }
+          // distance to the faces of the scanned box; faces clipped by the grid are infinitely far (nothing lives outside)
+          float b = INF;
+          if (xa > 0)               b = fminf(b, qx - (G.ox + (float)xa * G.cell));
+          if (xb < G.nx - 1)        b = fminf(b, (G.ox + (float)(xb + 1) * G.cell) - qx);
+          if (lcy - 1 > 0)          b = fminf(b, qy - (G.oy + (float)(lcy - 1) * G.cell));
+          if (lcy + 1 < G.ny - 1)   b = fminf(b, (G.oy + (float)(lcy + 2) * G.cell) - qy);
+          if (lcz - 1 > 0)          b = fminf(b, qz - (G.oz + (float)(lcz - 1) * G.cell));
+          if (lcz + 1 < G.nz - 1)   b = fminf(b, (G.oz + (float)(lcz + 2) * G.cell) - qz);
+          const float bs = b * 0.999f - 2e-3f;   // safety: float rounding of cell assignment / face positions
+          final_ok = (b == INF) || (bs > 0.f && key_dist(tt.k4) <= bs * bs) || bs >= gate_r;
+        }
+      }
+    }
+    if (part) {
+      done = true;
+      store_top5(a, p, tt);                       // the team pass reads the 5th distance as its search radius
+    }
+    const bool defer = part && !final_ok;
+    const unsigned dm = __ballot_sync(0xffffffffu, defer);
+    if (dm) {
+      unsigned int base = 0;
+      if (lane == 0) { base = atomicAdd(a.n_deferred, (unsigned int)__popc(dm)); n_def += __popc(dm); }
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (defer) a.deferred[base + __popc(dm & ((1u << lane) - 1u))] = (uint32_t)p;
+    }
+  }
+  if (a.n_fallback && lane == 0 && n_def) atomicAdd(a.n_fallback, n_def);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// team pass: 8 lanes per deferred query
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+  const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m), hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
+  return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long kmin(unsigned long long x, unsigned long long y) { return x < y ? x : y; }
+
+__global__ void __launch_bounds__(128) k_knn_team(SearchArgs a) {
+  const int lane = threadIdx.x & 31, team = lane >> 3, tl = lane & 7;
+  const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
+  const unsigned int nd = *a.n_deferred;
+  const GridDesc& G = a.grid;
+  const int* __restrict__ cs = G.cell_start;
+  const float gate_cap = a.gate_sq * TK_MARGIN;
+  for (unsigned int base = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4u; base < nd; base += nwarps * 4u) {
+    const unsigned int item = base + team;
+    const bool valid = item < nd;
+    int64_t p = 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f, T = 0.f;
+    if (valid) {
+      p = a.deferred[item];
+      const float4 q4 = a.pm[a.order[p]];
+      qx = q4.x; qy = q4.y; qz = q4.z;
+      T = fminf(a.knn_sqd[4 * a.Qt + p], gate_cap);      // the tile pass's 5th distance inside its box, or +inf
+    }
+    Top5 t;
+    top5_init(t);
+    float d4f = T;
+    if (valid) {
+      const float r = sqrtf(T) * 1.001f + 2e-3f;
+      const int ylo = max(cell_coord(qy - r, G.oy, G.inv_cell), 0), yhi = min(cell_coord(qy + r, G.oy, G.inv_cell), G.ny - 1);
+      const int zlo = max(cell_coord(qz - r, G.oz, G.inv_cell), 0), zhi = min(cell_coord(qz + r, G.oz, G.inv_cell), G.nz - 1);
+      const int nyr = yhi - ylo + 1, nzr = zhi - zlo + 1;
+      const int nrows = (nyr > 0 && nzr > 0) ? nyr * nzr : 0;
+      for (int ri = tl; ri < nrows; ri += 8) {
+        const int z = zlo + ri / nyr, y = ylo + ri % nyr;
+        // squared distance from the query to the (y,z) rectangle of this cell row, shrunk by the rounding margin
+        const float yl = G.oy + (float)y * G.cell, zl = G.oz + (float)z * G.cell;
+        const float dy = fmaxf(fmaxf(yl - qy, qy - (yl + G.cell)), 0.f), dz = fmaxf(fmaxf(zl - qz, qz - (zl + G.cell)), 0.f);
+        const float dys = fmaxf(dy * 0.999f - 2e-3f, 0.f), dzs = fmaxf(dz * 0.999f - 2e-3f, 0.f);
+        const float rem = d4f - (dys * dys + dzs * dzs);
+        if (rem < 0.f) continue;
+        const float rx = sqrtf(rem) * 1.001f + 2e-3f;
+        const int xl = max(cell_coord(qx - rx, G.ox, G.inv_cell), 0), xh = min(cell_coord(qx + rx, G.ox, G.inv_cell), G.nx - 1);
+        if (xl > xh) continue;
+        const int row = (z * G.ny + y) * G.nx;
+        const int s = __ldg(&cs[row + xl]), e = __ldg(&cs[row + xh + 1]);
+        for (int k = s; k < e; ++k) {
+          const float4 c = __ldg(&G.pts[k]);
+          const float d = l2_simple(qx, qy, qz, c.x, c.y, c.z);
+          if (d <= d4f) {
+            const unsigned long long key = make_key(d, __float_as_int(c.w));
+            if (key < t.k4) {
+              t.k4 = key; GLIO_KSWAP(t.k3, t.k4) GLIO_KSWAP(t.k2, t.k3) GLIO_KSWAP(t.k1, t.k2) GLIO_KSWAP(t.k0, t.k1)
+              d4f = fminf(d4f, key_dist(t.k4));
+            }
+          }
+        }
+      }
+    }
+    // merge the eight private lists: the five smallest of two sorted 5-lists are min(a_i, b_{4-i}); re-sort; three rounds
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) {
+      const unsigned long long b0 = shfl_xor_u64(t.k0, m), b1 = shfl_xor_u64(t.k1, m), b2 = shfl_xor_u64(t.k2, m), b3 = shfl_xor_u64(t.k3, m), b4 = shfl_xor_u64(t.k4, m);
+      t.k0 = kmin(t.k0, b4); t.k1 = kmin(t.k1, b3); t.k2 = kmin(t.k2, b2); t.k3 = kmin(t.k3, b1); t.k4 = kmin(t.k4, b0);
+      GLIO_KSWAP(t.k0, t.k1) GLIO_KSWAP(t.k3, t.k4) GLIO_KSWAP(t.k2, t.k4) GLIO_KSWAP(t.k2, t.k3) GLIO_KSWAP(t.k1, t.k4)
+      GLIO_KSWAP(t.k0, t.k3) GLIO_KSWAP(t.k0, t.k2) GLIO_KSWAP(t.k1, t.k3) GLIO_KSWAP(t.k1, t.k2)
+    }
+    if (valid && tl == 0) store_top5(a, p, t);
+  }
+}
+
+void knn_tile_run(const SearchArgs& sa, const PairRec* d_pairs, cudaStream_t st, LaunchCounter& lc) {
+  GLIO_REQUIRE(d_pairs != nullptr, GLIO_ERR_STATE, "knn_tile_run: the grid has no pair layout (build_pairs)");
+  const unsigned nb = (unsigned)((sa.Qt + 32 * TK_WARPS - 1) / (32 * TK_WARPS));
+  lc.begin("k_knn_tile", st); k_knn_tile<<<nb, 32 * TK_WARPS, 0, st>>>(sa, d_pairs); lc.end(st);
+  lc.begin("k_knn_team", st); k_knn_team<<<148 * 8, 128, 0, st>>>(sa); lc.end(st);
+  GLIO_CUDA_TRY(cudaGetLastError());
+}
+
+}  // namespace glio

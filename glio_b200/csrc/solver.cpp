@@ -286,8 +286,28 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval_user, SolverSumma
     sub_B[0] = dot(tmp, h0); sub_B[1] = dot(tmp, h1); sub_B[2] = sub_B[1]; sub_B[3] = dot(tmp2, h1);
     return true;
   };
+  // ---- Levenberg-Marquardt (levenberg_marquardt_strategy.cc:69-160).  `diag` holds the CLAMPED SQUARED column norms here
+  // (Ceres' diagonal_), `reuse` is reuse_diagonal_; the linear solve is (Hs + diag/radius) y = gs, step = -y: the normal
+  // equations of the regularised least-squares problem Ceres hands to its linear solver (DENSE_QR in the front end,
+  // dense_qr_solver.cc:120-153 - same minimiser, different rounding).
+  const bool lm = opt_.trust_region_strategy == 1;
+  double lm_decrease = 2.0;
+  auto lm_compute_step = [&]() -> int {
+    if (!reuse) for (int i = 0; i < n; ++i) diag[i] = std::min(std::max(Hs.at(i, i), opt_.min_lm_diagonal), opt_.max_lm_diagonal);
+    reuse = true;
+    A = Hs;
+    for (int i = 0; i < n; ++i) { const double d = std::sqrt(diag[i] / radius); A.at(i, i) += d * d; }
+    S.num_linear_solves++;
+    const auto tl0 = clk::now();
+    const bool ok = detail::cholesky_solve(A, gs.data(), y.data());
+    S.linear_solver_seconds += std::chrono::duration<double>(clk::now() - tl0).count();
+    if (!ok) return 1;
+    for (int i = 0; i < n; ++i) step[i] = -y[i];
+    return 0;
+  };
   // returns: 0 ok, 1 linear solver failure
   auto compute_step = [&]() -> int {
+    if (lm) return lm_compute_step();
     if (reuse) { if (opt_.dogleg_type == 0) traditional(); else subspace(); return 0; }
     reuse = true;
     for (int i = 0; i < n; ++i) diag[i] = std::sqrt(std::min(std::max(Hs.at(i, i), opt_.min_lm_diagonal), opt_.max_lm_diagonal));
@@ -361,7 +381,8 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval_user, SolverSumma
       if (++num_consecutive_invalid >= opt_.max_num_consecutive_invalid_steps) {
         S.termination = TERM_FAILURE; S.message = "Number of consecutive invalid steps more than max_num_consecutive_invalid_steps"; return;
       }
-      mu *= mu_inc; reuse = false;   // DoglegStrategy::StepIsInvalid
+      if (lm) { radius /= lm_decrease; lm_decrease *= 2.0; reuse = true; }   // LevenbergMarquardtStrategy::StepIsInvalid = StepRejected(0)
+      else { mu *= mu_inc; reuse = false; }                                   // DoglegStrategy::StepIsInvalid
       it.cost = x_cost; it.cost_change = 0; it.gradient_max_norm = prev.gradient_max_norm; it.gradient_norm = prev.gradient_norm;
       it.step_norm = 0; it.relative_decrease = 0; it.step_is_successful = 0;
       continue;
@@ -397,16 +418,25 @@ void TrustRegionDogleg::solve(double* x_io, const EvalFn& eval_user, SolverSumma
       apply_scaling();
       it.cost = x_cost; gradient_norms(it);
       it.step_is_successful = 1;
-      // DoglegStrategy::StepAccepted (:616-632)
-      if (it.relative_decrease < 0.25) radius *= 0.5;
-      if (it.relative_decrease > 0.75) radius = std::max(radius, 3.0 * dogleg_step_norm);
-      mu = std::max(min_mu, 2.0 * mu / mu_inc);
+      if (lm) {
+        // LevenbergMarquardtStrategy::StepAccepted (levenberg_marquardt_strategy.cc:143-150)
+        radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
+        radius = std::min(opt_.max_trust_region_radius, radius);
+        lm_decrease = 2.0;
+      } else {
+        // DoglegStrategy::StepAccepted (:616-632)
+        if (it.relative_decrease < 0.25) radius *= 0.5;
+        if (it.relative_decrease > 0.75) radius = std::max(radius, 3.0 * dogleg_step_norm);
+        mu = std::max(min_mu, 2.0 * mu / mu_inc);
+      }
       reuse = false;
       ev.accepted(cand_cost, model_cost_change);
     } else {
       // HandleUnsuccessfulStep (:773-778) + DoglegStrategy::StepRejected
       it.step_is_successful = 0;
-      radius *= 0.5; reuse = true;
+      if (lm) { radius /= lm_decrease; lm_decrease *= 2.0; }   // LevenbergMarquardtStrategy::StepRejected (:152-156)
+      else radius *= 0.5;
+      reuse = true;
       it.cost = cand_cost; it.gradient_max_norm = prev.gradient_max_norm; it.gradient_norm = prev.gradient_norm;
     }
   }

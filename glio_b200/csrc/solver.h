@@ -1,11 +1,14 @@
-// solver.h — host-side trust-region (dogleg) minimizer over normal equations, with Ceres 2.0.0 semantics.
+// solver.h — host-side trust-region minimizer (dogleg and Levenberg-Marquardt strategies) over normal equations, with
+// Ceres 2.0.0 semantics.
 //
 // The LiDAR residual blocks are evaluated on the device into 6x6 pose blocks; everything else the reference
 // adds to the same ceres::Problem (IMU, marginalisation prior, GNSS — host C++ CostFunctions by north_star)
 // arrives through a callback that accumulates into the same dense J^T J / J^T r.  This file restates, on the
 // normal equations, what ceres::Solve does for the options the reference sets (Estimator.cpp:2424-2433,
 // 3275-3284): TrustRegionMinimizer (ceres.tgz::internal/ceres/trust_region_minimizer.cc) with Jacobi scaling
-// (:231-263), DoglegStrategy (dogleg_strategy.cc:79-340,517-697; traditional and subspace),
+// (:231-263), DoglegStrategy (dogleg_strategy.cc:79-340,517-697; traditional and subspace), LevenbergMarquardtStrategy
+// (levenberg_marquardt_strategy.cc:69-160: D = sqrt(clamp(diag(J^T J)) / radius), radius / max(1/3, 1 - (2 rho - 1)^3) on
+// acceptance, radius / decrease_factor with the factor doubling on rejection),
 // normal-equation Cholesky (sparse_normal_cholesky_solver.cc:59-113), TrustRegionStepEvaluator
 // (trust_region_step_evaluator.cc) and QuaternionParameterization::Plus (local_parameterization.cc:163-182).
 // Quantities Ceres computes from the Jacobian itself (|J v|^2, (J s).(r + J s/2)) are computed from H = J^T J,
@@ -32,6 +35,8 @@ struct ParamBlock {
 struct SolverOptions {
   int max_num_iterations = 15;
   double max_solver_time_in_seconds = 1e9;   // Solver::Options::max_solver_time_in_seconds (LidarOdometry.cpp:527 sets 0.015)
+  int trust_region_strategy = 0;   // 0 DOGLEG (what Estimator.cpp:2427 / :3278 select), 1 LEVENBERG_MARQUARDT (Ceres' default, used by
+                                   // the front end's scan matcher, LidarOdometry.cpp:521-530)
   int dogleg_type = 0;  // 0 TRADITIONAL_DOGLEG, 1 SUBSPACE_DOGLEG
   bool use_nonmonotonic_steps = false;
   int max_consecutive_nonmonotonic_steps = 5;

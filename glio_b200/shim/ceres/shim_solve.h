@@ -179,8 +179,9 @@ inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summ
   so.min_lm_diagonal = options.min_lm_diagonal; so.max_lm_diagonal = options.max_lm_diagonal;
   so.max_num_consecutive_invalid_steps = options.max_num_consecutive_invalid_steps; so.jacobi_scaling = options.jacobi_scaling;
   so.function_tolerance = options.function_tolerance; so.gradient_tolerance = options.gradient_tolerance; so.parameter_tolerance = options.parameter_tolerance;
-  if (options.trust_region_strategy_type != DOGLEG)
-    S.message = "note: the glio shim implements the DOGLEG strategy (the only one GLIO selects); LEVENBERG_MARQUARDT requests run dogleg. ";
+  // LEVENBERG_MARQUARDT is Ceres' default and what the front end's scan matcher runs (LidarOdometry.cpp:521-530); DOGLEG is
+  // what the Estimator selects (Estimator.cpp:2427, :3278).  Both are implemented by the host minimizer.
+  so.trust_region_strategy = options.trust_region_strategy_type == LEVENBERG_MARQUARDT ? 1 : 0;
   glio::TrustRegionDogleg solver(blocks, so);
 
   std::vector<double> x(P.n_amb);

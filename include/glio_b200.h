@@ -187,7 +187,8 @@ typedef struct {
   double gradient_tolerance;             /* 1e-10 */
   double parameter_tolerance;            /* 1e-8 */
   int32_t fuse_candidate_jacobian;       /* 1: evaluate J with the candidate cost and reuse it on acceptance (same numbers, one pass less) */
-  int32_t reserved;
+  int32_t trust_region_strategy;         /* 0 DOGLEG (Estimator.cpp:2427, :3278), 1 LEVENBERG_MARQUARDT (Ceres' default: the front end's scan
+                                            matcher, LidarOdometry.cpp:521-530; ceres.tgz::internal/ceres/levenberg_marquardt_strategy.cc) */
 } glio_solver_options;
 void glio_default_solver_options(glio_solver_options* o);
 

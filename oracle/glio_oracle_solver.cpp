@@ -59,7 +59,8 @@ struct Opt {
   double initial_trust_region_radius, max_trust_region_radius, min_trust_region_radius, min_relative_decrease, min_lm_diagonal, max_lm_diagonal;
   int32_t max_num_consecutive_invalid_steps, jacobi_scaling;
   double function_tolerance, gradient_tolerance, parameter_tolerance;
-  int32_t fuse_candidate_jacobian, reserved;
+  int32_t fuse_candidate_jacobian, reserved;   /* reserved = trust region strategy: 0 DOGLEG, 1 LEVENBERG_MARQUARDT over normal-equation Cholesky,
+                                                  2 LEVENBERG_MARQUARDT over DENSE_QR (the front end's options, LidarOdometry.cpp:521-530) */
 };
 struct Iter { int32_t iteration, step_is_valid, step_is_successful, reserved; double cost, cost_change, gradient_max_norm, gradient_norm, step_norm, relative_decrease, trust_region_radius, mu; };
 struct Summary { int32_t termination, num_iterations, num_successful_steps, num_unsuccessful_steps, num_evaluations, num_jacobian_evaluations, num_linear_solves, num_valid_steps; double initial_cost, final_cost; char message[128]; };
@@ -249,6 +250,38 @@ bool dense_cholesky_solve(std::vector<double>& A, int n, const double* b, double
 
 // real parts of all roots of a quartic (highest power first) — Aberth/Durand-Kerner; what
 // FindPolynomialRoots(poly, &real, NULL) returns in ceres.tgz::internal/ceres/polynomial.cc
+// min |A x - b| for a dense row-major m x n matrix (m >= n) by unpivoted Householder QR: what Ceres' DENSE_QR does with the
+// LM-augmented Jacobian [J; D] and [r; 0] (ceres.tgz::internal/ceres/dense_qr_solver.cc:120-153, Eigen householderQr().solve()).
+bool dense_qr_solve(std::vector<double>& A, int64_t m, int n, std::vector<double>& b, double* x) {
+  for (int k = 0; k < n; ++k) {
+    double tail = 0; for (int64_t i = k + 1; i < m; ++i) tail += A[(size_t)i * n + k] * A[(size_t)i * n + k];
+    const double c0 = A[(size_t)k * n + k];
+    double beta, tau;
+    if (tail <= std::numeric_limits<double>::min()) { tau = 0; beta = c0; }
+    else {
+      beta = std::sqrt(c0 * c0 + tail); if (c0 >= 0) beta = -beta;
+      const double den = c0 - beta;
+      for (int64_t i = k + 1; i < m; ++i) A[(size_t)i * n + k] /= den;
+      tau = (beta - c0) / beta;
+    }
+    A[(size_t)k * n + k] = beta;
+    if (tau != 0) {
+      for (int j = k + 1; j < n; ++j) {
+        double t = A[(size_t)k * n + j]; for (int64_t i = k + 1; i < m; ++i) t += A[(size_t)i * n + k] * A[(size_t)i * n + j];
+        A[(size_t)k * n + j] -= tau * t; for (int64_t i = k + 1; i < m; ++i) A[(size_t)i * n + j] -= tau * A[(size_t)i * n + k] * t;
+      }
+      double t = b[k]; for (int64_t i = k + 1; i < m; ++i) t += A[(size_t)i * n + k] * b[i];
+      b[k] -= tau * t; for (int64_t i = k + 1; i < m; ++i) b[i] -= tau * A[(size_t)i * n + k] * t;
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double sacc = b[i]; for (int j = i + 1; j < n; ++j) sacc -= A[(size_t)i * n + j] * x[j];
+    x[i] = sacc / A[(size_t)i * n + i];
+  }
+  for (int i = 0; i < n; ++i) if (!std::isfinite(x[i])) return false;
+  return true;
+}
+
 bool poly_real_parts(const double* p5, std::vector<double>* out) {
   out->clear(); int lead = 0; while (lead < 5 && p5[lead] == 0.0) ++lead; int deg = 4 - lead; if (deg < 1) return false;
   typedef std::complex<double> cd; std::vector<cd> c(deg + 1); for (int i = 0; i <= deg; ++i) c[i] = p5[lead + i] / p5[lead];
@@ -402,7 +435,33 @@ int go_problem_solve(void* h, const void* options, int mode, int nthreads, void*
     sB[0] = dotv(j0, j0); sB[1] = dotv(j0, j1); sB[2] = sB[1]; sB[3] = dotv(j1, j1);
     return true;
   };
+  // LevenbergMarquardtStrategy::ComputeStep (ceres.tgz::internal/ceres/levenberg_marquardt_strategy.cc:69-141)
+  const int strategy = o.reserved; double lm_decrease = 2.0;
+  auto lm_step = [&]() -> int {
+    if (!reuse) { sq_col_norm(P, diag.data()); for (int i = 0; i < n; ++i) diag[i] = std::min(std::max(diag[i], o.min_lm_diagonal), o.max_lm_diagonal); }
+    reuse = true;
+    std::vector<double> lmd(n); for (int i = 0; i < n; ++i) lmd[i] = std::sqrt(diag[i] / radius);
+    S.num_linear_solves++;
+    bool ok;
+    if (strategy == 2) {
+      const int64_t m = P.nrows + n;
+      std::vector<double> Aug((size_t)m * n, 0.0), baug((size_t)m, 0.0);
+      for (int64_t i = 0; i < P.nrows; ++i) { for (int64_t p = P.rowptr[i]; p < P.rowptr[i + 1]; ++p) Aug[(size_t)i * n + P.col[p]] += P.val[p]; baug[i] = P.r[i]; }
+      for (int i = 0; i < n; ++i) Aug[(size_t)(P.nrows + i) * n + i] = lmd[i];
+      ok = dense_qr_solve(Aug, m, n, baug, y.data());
+    } else {
+      std::fill(rhs.begin(), rhs.end(), 0.0); left_multiply(P, P.r.data(), rhs.data());
+      std::fill(A.begin(), A.end(), 0.0);
+      for (int64_t i = 0; i < P.nrows; ++i) for (int64_t p = P.rowptr[i]; p < P.rowptr[i + 1]; ++p) for (int64_t q = P.rowptr[i]; q < P.rowptr[i + 1]; ++q) A[(size_t)P.col[p] * n + P.col[q]] += P.val[p] * P.val[q];
+      for (int i = 0; i < n; ++i) A[(size_t)i * n + i] += lmd[i] * lmd[i];
+      ok = dense_cholesky_solve(A, n, rhs.data(), y.data());
+    }
+    if (!ok) return 1;
+    for (int i = 0; i < n; ++i) step[i] = -y[i];
+    return 0;
+  };
   auto compute_step = [&]() -> int {
+    if (strategy != 0) return lm_step();
     if (reuse) { if (o.dogleg_type == 0) traditional(); else subspace(); return 0; }
     reuse = true;
     sq_col_norm(P, diag.data());
@@ -450,7 +509,8 @@ int go_problem_solve(void* h, const void* options, int mode, int nthreads, void*
     it.step_is_valid = valid;
     if (!valid) {
       if (++ninvalid >= o.max_num_consecutive_invalid_steps) { S.termination = 2; snprintf(S.message, sizeof(S.message), "Number of consecutive invalid steps more than max"); break; }
-      mu *= 10.0; reuse = false; it.cost = x_cost; it.gradient_max_norm = prev.gradient_max_norm; it.gradient_norm = prev.gradient_norm; continue;
+      if (strategy != 0) { radius /= lm_decrease; lm_decrease *= 2.0; reuse = true; } else { mu *= 10.0; reuse = false; }
+      it.cost = x_cost; it.gradient_max_norm = prev.gradient_max_norm; it.gradient_norm = prev.gradient_norm; continue;
     }
     steps.insert(steps.end(), delta.begin(), delta.end());
     plus(P, x.data(), delta.data(), cand.data());
@@ -475,15 +535,21 @@ int go_problem_solve(void* h, const void* options, int mode, int nthreads, void*
       x = cand; { double s2 = 0; for (int i = 0; i < na; ++i) s2 += x[i] * x[i]; x_norm = std::sqrt(s2); }
       if (!eval_grad_jac(it, false)) { S.termination = 2; snprintf(S.message, sizeof(S.message), "Residual and Jacobian evaluation failed."); break; }
       it.step_is_successful = 1;
-      if (it.relative_decrease < 0.25) radius *= 0.5;
-      if (it.relative_decrease > 0.75) radius = std::max(radius, 3.0 * dogleg_step_norm);
-      mu = std::max(1e-8, 2.0 * mu / 10.0); reuse = false;
+      if (strategy != 0) {   // LevenbergMarquardtStrategy::StepAccepted (:143-150)
+        radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
+        radius = std::min(o.max_trust_region_radius, radius); lm_decrease = 2.0;
+      } else {
+        if (it.relative_decrease < 0.25) radius *= 0.5;
+        if (it.relative_decrease > 0.75) radius = std::max(radius, 3.0 * dogleg_step_norm);
+        mu = std::max(1e-8, 2.0 * mu / 10.0);
+      }
+      reuse = false;
       se_cur = cand_cost; se_acc_cand += model_cost_change; se_acc_ref += model_cost_change;
       if (se_cur < se_min) { se_min = se_cur; se_n = 0; se_cand = se_cur; se_acc_cand = 0.0; }
       else { ++se_n; if (se_cur > se_cand) { se_cand = se_cur; se_acc_cand = 0.0; } }
       if (se_n == se_max) { se_ref = se_cand; se_acc_ref = se_acc_cand; }
     } else {
-      it.step_is_successful = 0; radius *= 0.5; reuse = true; it.cost = cand_cost; it.gradient_max_norm = prev.gradient_max_norm; it.gradient_norm = prev.gradient_norm;
+      it.step_is_successful = 0; if (strategy != 0) { radius /= lm_decrease; lm_decrease *= 2.0; } else radius *= 0.5; reuse = true; it.cost = cand_cost; it.gradient_max_norm = prev.gradient_max_norm; it.gradient_norm = prev.gradient_norm;
     }
   }
 done:

@@ -55,7 +55,7 @@ static void report(const char* name, bool ok, const std::vector<double>& x) {
 // Jacobian exactly as the test writes them, including its (1 - x4) / (x1 - 1) factors in the f4 column entries) is
 // transcribed literally; g = J^T r as the strategy computes it.  Default Solver::Options: 50 iterations, traditional
 // dogleg, Jacobi scaling on; tolerances 1e-26, radius 1e4 / 1e20, lm diagonal 1e-6 / 1e32 (:218-236).
-static bool powell_case(bool c1, bool c2, bool c3, bool c4, double out[4]) {
+static bool powell_case(bool c1, bool c2, bool c3, bool c4, double out[4], int strategy = 0) {
   const bool col[4] = {c1, c2, c3, c4};
   int map[4], n = 0;
   for (int k = 0; k < 4; ++k) map[k] = col[k] ? n++ : -1;
@@ -63,7 +63,7 @@ static bool powell_case(bool c1, bool c2, bool c3, bool c4, double out[4]) {
   for (int k = 0; k < 4; ++k) if (!col[k]) p0[k] = 0.0;
   std::vector<glio::ParamBlock> blocks{glio::ParamBlock{0, n, 0, n, false, nullptr}};
   glio::SolverOptions o;
-  o.max_num_iterations = 50; o.dogleg_type = 0;
+  o.max_num_iterations = 50; o.dogleg_type = 0; o.trust_region_strategy = strategy;
   o.initial_trust_region_radius = 1e4; o.max_trust_region_radius = 1e20; o.min_lm_diagonal = 1e-6; o.max_lm_diagonal = 1e32;
   o.function_tolerance = 1e-26; o.gradient_tolerance = 1e-26; o.parameter_tolerance = 1e-26; o.jacobi_scaling = true;
   glio::TrustRegionDogleg solver(blocks, o);
@@ -160,6 +160,62 @@ int main() {
     const bool ok = powell_case(cases[c][0], cases[c][1], cases[c][2], cases[c][3], out);
     char name[64]; snprintf(name, sizeof(name), "Powell_%d%d%d%d", (int)cases[c][0], (int)cases[c][1], (int)cases[c][2], (int)cases[c][3]);
     report(name, ok, std::vector<double>(out, out + 4));
+  }
+  // PowellsSingularFunctionUsingLevenbergMarquardt (trust_region_minimizer_test.cc:257-280): the 14 column activations Ceres runs
+  const bool lm_cases[14][4] = {{1, 1, 1, 1}, {1, 1, 1, 0}, {1, 0, 1, 1}, {0, 1, 1, 1}, {1, 1, 0, 0}, {1, 0, 1, 0}, {0, 1, 1, 0}, {1, 0, 0, 1}, {0, 1, 0, 1}, {0, 0, 1, 1}, {1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+  for (int c = 0; c < 14; ++c) {
+    double out[4];
+    const bool ok = powell_case(lm_cases[c][0], lm_cases[c][1], lm_cases[c][2], lm_cases[c][3], out, 1);
+    char name[64]; snprintf(name, sizeof(name), "PowellLM_%d%d%d%d", (int)lm_cases[c][0], (int)lm_cases[c][1], (int)lm_cases[c][2], (int)lm_cases[c][3]);
+    report(name, ok, std::vector<double>(out, out + 4));
+  }
+  {  // LevenbergMarquardtStrategy radius rule (levenberg_marquardt_strategy_test.cc:80-112, AcceptRejectStepRadiusScaling) driven
+     // through the minimizer: a 1-D problem whose evaluator returns scripted costs so that the step qualities are exactly
+     // rejected, rejected, 1, 1, 0.25, 1, 1, 1 with initial radius 2 and max radius 20 -> radii 1, 0.25, 0.75, 2.25, 2, 6, 18, 20.
+     // With H = 1, g = -1 (r = x - 1 at x = 0 ... kept constant), the LM step is s = 1 / (1 + 1/radius) and the model decrease
+     // is s - s*s/2; the scripted candidate cost = cost - quality * model decrease.
+    std::vector<glio::ParamBlock> blocks{glio::ParamBlock{0, 1, 0, 1, false, nullptr}};
+    glio::SolverOptions o; o.trust_region_strategy = 1; o.max_num_iterations = 8; o.initial_trust_region_radius = 2.0; o.max_trust_region_radius = 20.0;
+    o.min_lm_diagonal = 1.0; o.max_lm_diagonal = 1.0; o.jacobi_scaling = false; o.function_tolerance = 0; o.gradient_tolerance = 0; o.parameter_tolerance = 0;
+    o.fuse_candidate_jacobian = false; o.min_relative_decrease = 1e-3;
+    const double quality[8] = {-0.5, -1.0, 1.0, 1.0, 0.25, 1.0, 1.0, 1.0};   // (a quality of exactly 0 would trip the function tolerance test first)
+    const double radii[9] = {2.0, 1.0, 0.25, 0.75, 2.25, 2.0, 6.0, 18.0, 20.0};
+    int k = 0; double cur_cost = 100.0;
+    glio::EvalFn eval = [&](const double* x, bool want_jac, double* cost, BandMat* H, double* g) -> bool {
+      if (want_jac) { *cost = cur_cost; H->reset(1, 0); H->at(0, 0) = 1.0; g[0] = -1.0; return true; }
+      const double s = 1.0 / (1.0 + 1.0 / radii[k]), dec = s - 0.5 * s * s;
+      const double cand = cur_cost - quality[k] * dec;
+      if (quality[k] > 1e-3) cur_cost = cand;
+      ++k; *cost = cand; return true;
+    };
+    std::vector<double> x0(1, 0.0); glio::SolverSummary S;
+    glio::TrustRegionDogleg solver(blocks, o);
+    solver.solve(x0.data(), eval, &S);
+    bool ok = S.iterations.size() == 9; std::vector<double> got;
+    for (size_t i = 0; i < S.iterations.size(); ++i) { got.push_back(S.iterations[i].trust_region_radius); if (i < 9) ok = ok && std::fabs(S.iterations[i].trust_region_radius - radii[i]) <= 1e-12 * radii[i]; }
+    report("LM_AcceptRejectStepRadiusScaling", ok, got);
+  }
+  {  // CorrectDiagonalToLinearSolver (levenberg_marquardt_strategy_test.cc:114-160): J = [[0 1 100],[0 1 0]], min/max_lm_diagonal 1e-2 / 1e2,
+     // radius 2 -> D^2 = {1e-2, 2, 1e2} / 2 on the diagonal of the regularised normal equations; the first LM step must equal
+     // -(J^T J + D^2)^-1 J^T r computed independently.
+    std::vector<glio::ParamBlock> blocks{glio::ParamBlock{0, 3, 0, 3, false, nullptr}};
+    glio::SolverOptions o; o.trust_region_strategy = 1; o.max_num_iterations = 1; o.initial_trust_region_radius = 2.0; o.max_trust_region_radius = 20.0;
+    o.min_lm_diagonal = 1e-2; o.max_lm_diagonal = 1e2; o.jacobi_scaling = false; o.function_tolerance = 0; o.gradient_tolerance = 0; o.parameter_tolerance = 0;
+    const double Jm[2][3] = {{0.0, 1.0, 100.0}, {0.0, 1.0, 0.0}}, r0[2] = {1.0, 1.0};
+    glio::EvalFn eval = [&](const double* x, bool want_jac, double* cost, BandMat* H, double* g) -> bool {
+      double r[2]; for (int i = 0; i < 2; ++i) { r[i] = r0[i]; for (int j = 0; j < 3; ++j) r[i] += Jm[i][j] * x[j]; }
+      *cost = 0.5 * (r[0] * r[0] + r[1] * r[1]);
+      if (want_jac) { H->reset(3, 2); for (int a = 0; a < 3; ++a) { g[a] = Jm[0][a] * r[0] + Jm[1][a] * r[1]; for (int b = 0; b <= a; ++b) H->at(a, b) = Jm[0][a] * Jm[0][b] + Jm[1][a] * Jm[1][b]; } }
+      return true;
+    };
+    std::vector<double> x0(3, 0.0); glio::SolverSummary S;
+    glio::TrustRegionDogleg solver(blocks, o);
+    solver.solve(x0.data(), eval, &S);
+    // independent 3x3 solve: A = J^T J + diag(1e-2, 2, 1e2)/2 ; x0 column decouples (A00 = 0.005, g0 = 0)
+    const double A11 = 2.0 + 1.0, A12 = 100.0, A22 = 10000.0 + 50.0, g1 = 2.0, g2 = 100.0;
+    const double det = A11 * A22 - A12 * A12; const double e1 = -(A22 * g1 - A12 * g2) / det, e2 = -(-A12 * g1 + A11 * g2) / det;
+    bool ok = S.steps.size() >= 3 && std::fabs(S.steps[0]) <= 1e-15 && std::fabs(S.steps[1] - e1) <= 1e-12 * std::fabs(e1) + 1e-15 && std::fabs(S.steps[2] - e2) <= 1e-12 * std::fabs(e2);
+    report("LM_CorrectDiagonalToLinearSolver", ok, S.steps);
   }
   {  // Solver::Options::max_solver_time_in_seconds (trust_region_minimizer.cc:327-329, :605-619): a zero budget stops the
      // solve before the first step with NO_CONVERGENCE, as the reference's front end relies on (LidarOdometry.cpp:527)

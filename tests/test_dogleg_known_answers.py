@@ -19,6 +19,10 @@ def test_ceres_dogleg_strategy_known_answers(tmp_path):
     # trust_region_minimizer_test.cc: PowellsSingularFunctionUsingDogleg, the 13 column activations Ceres runs
     assert [n for n in names if n.startswith("Powell_")] == ["Powell_1110", "Powell_1011", "Powell_0111", "Powell_1100", "Powell_1010", "Powell_0110",
                                                               "Powell_1001", "Powell_0101", "Powell_0011", "Powell_1000", "Powell_0100", "Powell_0010", "Powell_0001"]
+    # trust_region_minimizer_test.cc:257-280 PowellsSingularFunctionUsingLevenbergMarquardt (14 activations) and
+    # levenberg_marquardt_strategy_test.cc (radius scaling, diagonal handed to the linear solver)
+    assert len([n for n in names if n.startswith("PowellLM_")]) == 14
+    assert "LM_AcceptRejectStepRadiusScaling" in names and "LM_CorrectDiagonalToLinearSolver" in names
     # polynomial_test.cc: the root finder of the subspace dogleg
     assert len([n for n in names if n.startswith("Poly_")]) == 11
     bad = [l for l in out if l.split()[1] != "ok"]
