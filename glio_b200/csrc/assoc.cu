@@ -560,7 +560,7 @@ void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const Assoc
   GLIO_CUDA_TRY(cudaMemsetAsync(w.n_deferred, 0, sizeof(unsigned int), st));
   const unsigned ns = (unsigned)((Qt + 32 * KNN_WARPS - 1) / (32 * KNN_WARPS));
   if (w.knn_mode == 4) {
-    knn_tile_run(sa, gb.pairs.p, st, lc);
+    knn_tile_run(sa, gb.pairs.p, cell_count, scan_tmp, st, lc);      // cell_count is free again after the query scatter
   } else if (w.knn_mode == 2 || w.knn_mode == 3) {
     lc.begin("k_knn_box", st);
     if (w.knn_mode == 3) k_knn_box<true><<<(unsigned)((Qt + 127) / 128), 128, 0, st>>>(sa);

@@ -71,6 +71,6 @@ __device__ __forceinline__ void store_top5(const SearchArgs& a, int64_t p, const
 }
 
 // K1a, staged tile search + team pass (knn_tile.cu, GLIO_KNN_MODE=4)
-void knn_tile_run(const SearchArgs& sa, const PairRec* d_pairs, cudaStream_t st, LaunchCounter& lc);
+void knn_tile_run(const SearchArgs& sa, const PairRec* d_pairs, DevBuf<int>& work, DevBuf<int>& scan_tmp, cudaStream_t st, LaunchCounter& lc);
 
 }  // namespace glio

@@ -11,22 +11,31 @@
 //               neighbour distance from above (five distinct candidates are at least that close)
 //       pass B  packed distances again, candidates under the bound (x 1+1e-6: the packed arithmetic is fused) set a bit in
 //               a per-lane survivor mask (16 candidates per word, parked in shared memory; about 6-9 survive of ~190)
-//       flush   survivors re-evaluated with the exact FLANN L2_Simple<float> order and inserted in the (distance, index)
-//               top-5 -> the only place a result is decided, so indices and distances stay bit-exact
-//   * a lane whose 5th distance is provably inside the scanned box is final; the rest (sparse map, displaced query,
-//     oversized tile) go to the team pass with their 5th distance as the search radius.
-//   * team pass (k_knn_team): 8 lanes per deferred query split the cell rows of the sphere's bounding box (rows clipped
-//     to the circle the sphere cuts out of them), private top-5 each, merged with three shuffle rounds (half-cleaner +
-//     5-sorter per round).
+//       flush   the mask bits are compacted into a dense per-lane list (cheap divergent loop), then the survivors are
+//               re-evaluated with the exact FLANN L2_Simple<float> order and inserted in the (distance, index) top-5
+//               -> the only place a result is decided, so indices and distances stay bit-exact
+//   * a lane whose 5th distance is provably inside the scanned box is final; the rest (sparse map, query displaced from the
+//     surface by the pose error, oversized tile) are DEFERRED with their 5th distance as a proven search radius.
+//   * second pass (k_knn_tile2): the deferred queries, compacted IN SORTED ORDER, form tiles again; a tile's box is the union
+//     of its lanes' search spheres (so every lane is final afterwards), staged nine rows at a time; no pass A is needed
+//     because the radius is already a bound.  What does not fit the staging buffer falls back to
+//   * the team pass (k_knn_team): 8 lanes per query split the cell rows of the sphere's bounding box, private top-5 each,
+//     merged with three shuffle rounds (half-cleaner + 5-sorter).  Normally (almost) empty.
 // Compiled with -fmad=false like assoc.cu; the packed helpers are pre-filters only (knn_common.cuh).
 #include "knn_common.cuh"
 
 namespace glio {
 
 constexpr int TK_WARPS = 4;          // warps (= tiles in flight) per CTA
-constexpr int TK_CAP_PAIRS = 256;    // staged pair records per tile (512 map points, 8 KB); larger tiles are deferred
-constexpr int TK_SPAN = 12;          // max x-extent (cells) of the queries sharing one tile
+constexpr int TK_CAP_PAIRS = 224;    // staged pair records per tile (448 map points, 7 KB); larger tiles are split / deferred
+constexpr int TK_WORDS = TK_CAP_PAIRS / 8 + 1;
+constexpr int TK_LIST = 16;          // per-lane survivor list capacity (more survivors are pushed straight from the mask loop)
+constexpr int TK_SPAN = 12;          // max x-extent (cells) of the queries sharing one tile (first pass)
+constexpr int TK_SPAN2 = 8;          // same, second pass
 constexpr float TK_MARGIN = 1.000002f;
+constexpr float TK_WIDE_CELLS = 2.5f;  // second pass: search radius (in cells) above which a query is handed to the team pass
+constexpr int TK_SMEM_WARP = (TK_CAP_PAIRS + 8) * 32 + TK_WORDS * 64 + TK_LIST * 64;   // bytes per warp
+constexpr int TK_SMEM = TK_WARPS * TK_SMEM_WARP + TK_WARPS * 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -62,52 +71,170 @@ __device__ __forceinline__ float fifth_of_8(float m0, float m1, float m2, float 
   return m4;
 }
 
-__global__ void __launch_bounds__(32 * TK_WARPS) k_knn_tile(SearchArgs a, const PairRec* __restrict__ gpairs) {
-  __shared__ __align__(128) PairRec s_tile[TK_WARPS][TK_CAP_PAIRS + 8];
-  __shared__ uint16_t s_mask[TK_WARPS][(TK_CAP_PAIRS / 8 + 1) * 32];
-  __shared__ __align__(8) unsigned long long s_bar[TK_WARPS];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t p = ((int64_t)blockIdx.x * TK_WARPS + wid) * 32 + lane;
-  const bool active = p < a.Qt;
-  const GridDesc& G = a.grid;
-  const float INF = __int_as_float(0x7f800000);
-  PairRec* tile = s_tile[wid];
-  uint16_t* mask = s_mask[wid] + lane;
-  unsigned long long* bar = &s_bar[wid];
+// per-warp staging area
+struct WarpTile {
+  PairRec* tile;              // [TK_CAP_PAIRS + 8]
+  uint16_t* mask;             // [TK_WORDS][32], already offset by the lane
+  uint16_t* list;             // [TK_LIST][32], already offset by the lane
+  unsigned long long* bar;
+  unsigned parity;
+};
+
+__device__ __forceinline__ WarpTile warp_tile_init(unsigned char* smem, int wid, int lane) {
+  WarpTile wt;
+  unsigned char* base = smem + (size_t)wid * TK_SMEM_WARP;
+  wt.tile = reinterpret_cast<PairRec*>(base);
+  wt.mask = reinterpret_cast<uint16_t*>(base + (TK_CAP_PAIRS + 8) * 32) + lane;
+  wt.list = reinterpret_cast<uint16_t*>(base + (TK_CAP_PAIRS + 8) * 32 + TK_WORDS * 64) + lane;
+  wt.bar = reinterpret_cast<unsigned long long*>(smem + (size_t)TK_WARPS * TK_SMEM_WARP) + wid;
+  wt.parity = 0;
   if (lane == 0) {
-    mbar_init(bar, 1);
+    mbar_init(wt.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   fence_proxy_async();
   __syncwarp();
+  return wt;
+}
+
+// Stage up to nine cell rows: lanes 0..8 hold one row's point range [s, e) of the sorted map each (s == e: nothing).  All 32
+// lanes must call.  Returns the padded number of pair records staged (a multiple of 8; 0: nothing to scan), or -1 when the
+// rows do not fit the buffer (nothing staged).
+__device__ __forceinline__ int stage_rows(WarpTile& wt, const PairRec* __restrict__ gpairs, int lane, int s, int e) {
+  const int ps = s >> 1;
+  const int np = e > s ? ((e + 1) >> 1) - ps : 0;
+  int off = np;
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += v; }
+  const int total = __shfl_sync(0xffffffffu, off, 15);
+  off -= np;
+  if (total > TK_CAP_PAIRS) return -1;
+  if (total == 0) return 0;
+  fence_proxy_async();              // earlier generic-proxy accesses of this buffer (previous tile) before the async writes
+  __syncwarp();
+  if (lane == 0) mbar_expect_tx(wt.bar, (unsigned)total * 32u);
+  __syncwarp();
+  if (np > 0) bulk_g2s(wt.tile + off, gpairs + ps, (unsigned)np * 32u, wt.bar);
+  mbar_wait(wt.bar, wt.parity);
+  wt.parity ^= 1u;
+  // the pair run of a row may start / end with a half-record of the neighbouring cell: neutralise it
+  if (np > 0) {
+    if (s & 1) { wt.tile[off].x0 = PAIR_FAR; wt.tile[off].i0 = 0x7fffffff; }
+    if (e & 1) { wt.tile[off + np - 1].x1 = PAIR_FAR; wt.tile[off + np - 1].i1 = 0x7fffffff; }
+  }
+  const int npad = (total + 7) & ~7;
+  if (lane < npad - total) {
+    PairRec f; f.x0 = PAIR_FAR; f.x1 = PAIR_FAR; f.y0 = 0.f; f.y1 = 0.f; f.z0 = 0.f; f.z1 = 0.f; f.i0 = 0x7fffffff; f.i1 = 0x7fffffff;
+    wt.tile[total + lane] = f;
+  }
+  __syncwarp();
+  return npad;
+}
+
+// packed squared distances of the query to the two points of a pair record (fused arithmetic: a pre-filter, not a result)
+__device__ __forceinline__ void pair_dist(const ulonglong2* T2, int k, f32x2_t nqx2, f32x2_t nqy2, f32x2_t nqz2, float& d0, float& d1) {
+  const f32x2_t one2 = 0x3f8000003f800000ull;
+  const ulonglong2 xy = T2[2 * k];
+  const unsigned long long zz = *reinterpret_cast<const unsigned long long*>(&T2[2 * k + 1]);
+  // p - q through the FMA pipe (p * 1 + (-q)); the ALU pipe is the busy one in this kernel
+  const f32x2_t dx = fma2(xy.x, one2, nqx2), dy = fma2(xy.y, one2, nqy2), dz = fma2(zz, one2, nqz2);
+  unpack2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), d0, d1);
+}
+
+struct QueryRegs { float qx, qy, qz; f32x2_t nqx2, nqy2, nqz2; };
+__device__ __forceinline__ QueryRegs make_query(float qx, float qy, float qz) {
+  QueryRegs q; q.qx = qx; q.qy = qy; q.qz = qz; q.nqx2 = pack2(-qx, -qx); q.nqy2 = pack2(-qy, -qy); q.nqz2 = pack2(-qz, -qz); return q;
+}
+
+// exact distance of staged candidate j to the query, pushed into the top-5
+__device__ __forceinline__ void push_exact(const WarpTile& wt, int j, const QueryRegs& q, Top5& tt) {
+  const float* rec = reinterpret_cast<const float*>(wt.tile) + (j >> 1) * 8 + (j & 1);
+  const int id = __float_as_int(rec[6]);
+  top5_push(tt, l2_simple(q.qx, q.qy, q.qz, rec[0], rec[2], rec[4]), id);
+}
+
+// pass B + flush for the calling lane (no warp-level synchronisation inside: callers may be a subset of the warp)
+__device__ __forceinline__ void filter_and_flush(const WarpTile& wt, int npad, const QueryRegs& q, float thr, Top5& tt) {
+  const ulonglong2* T2 = reinterpret_cast<const ulonglong2*>(wt.tile);
+  const int nwords = npad >> 3;
+#pragma unroll 1
+  for (int w = 0; w < nwords; ++w) {
+    unsigned m = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float d0, d1;
+      pair_dist(T2, 8 * w + u, q.nqx2, q.nqy2, q.nqz2, d0, d1);
+      if (d0 <= thr) m |= 1u << (2 * u);
+      if (d1 <= thr) m |= 2u << (2 * u);
+    }
+    wt.mask[w * 32] = (uint16_t)m;
+  }
+  // mask bits -> dense per-lane list (short divergent loop), then a dense exact pass
+  int cnt = 0;
+#pragma unroll 1
+  for (int w = 0; w < nwords; ++w) {
+    unsigned m = wt.mask[w * 32];
+    while (m) {
+      const int j = 16 * w + __ffs(m) - 1;
+      m &= m - 1;
+      if (cnt < TK_LIST) { wt.list[cnt * 32] = (uint16_t)j; ++cnt; }
+      else push_exact(wt, j, q, tt);                       // list full (rare: loose bound): straight from the mask loop
+    }
+  }
+#pragma unroll 1
+  for (int i = 0; i < cnt; ++i) push_exact(wt, wt.list[i * 32], q, tt);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// first pass: one warp per 32 consecutive (cell-sorted) queries
+// ---------------------------------------------------------------------------------------------------------------------
+struct TileArgs {
+  SearchArgs sa;
+  const PairRec* pairs;
+  unsigned int* dmask;      // [nwarps] lanes deferred by each warp of the first pass
+  int* dcount;              // [nwarps + 1] their number (scanned into dpos)
+  const int* dpos;          // [nwarps + 1] exclusive scan of dcount; dpos[nwarps] = number of deferred queries
+  int nwarps;
+  uint32_t* fb_list;        // fallback list of the second pass (team pass input)
+  unsigned int* n_fb;
+};
+
+__global__ void __launch_bounds__(32 * TK_WARPS) k_knn_tile(TileArgs ta) {
+  extern __shared__ __align__(128) unsigned char tk_smem[];
+  const SearchArgs& a = ta.sa;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int gw = blockIdx.x * TK_WARPS + wid;
+  const int64_t p = (int64_t)gw * 32 + lane;
+  const bool active = p < a.Qt;
+  const GridDesc& G = a.grid;
+  const float INF = __int_as_float(0x7f800000);
+  WarpTile wt = warp_tile_init(tk_smem, wid, lane);
 
   float qx = 0.f, qy = 0.f, qz = 0.f;
   if (active) { const float4 q4 = a.pm[a.order[p]]; qx = q4.x; qy = q4.y; qz = q4.z; }
+  const QueryRegs q = make_query(qx, qy, qz);
   const int cx = cell_coord(qx, G.ox, G.inv_cell), cy = cell_coord(qy, G.oy, G.inv_cell), cz = cell_coord(qz, G.oz, G.inv_cell);
   const float gate_r = sqrtf(a.gate_sq) + 2e-3f;
   const int rmax = (int)ceilf(gate_r * G.inv_cell) + 1;
   // far outside the grid: nothing within the gate radius
   const bool far_out = cx < -rmax || cy < -rmax || cz < -rmax || cx >= G.nx + rmax || cy >= G.ny + rmax || cz >= G.nz + rmax;
-  Top5 t;
-  top5_init(t);
-  if (active && far_out) store_top5(a, p, t);
+  if (active && far_out) { Top5 t; top5_init(t); store_top5(a, p, t); }
   bool done = !active || far_out;
-  const f32x2_t qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
+  bool deferred = false;
   const float gate_cap = a.gate_sq * TK_MARGIN;
   const int* __restrict__ cs = G.cell_start;
-  unsigned parity = 0;
-  unsigned long long n_def = 0;
+  int span_lim = TK_SPAN;
 
   for (;;) {
     const unsigned pending = __ballot_sync(0xffffffffu, !done);
     if (!pending) break;
     const int leader = __ffs(pending) - 1;
     const int lcx = __shfl_sync(0xffffffffu, cx, leader), lcy = __shfl_sync(0xffffffffu, cy, leader), lcz = __shfl_sync(0xffffffffu, cz, leader);
-    const bool part = !done && cy == lcy && cz == lcz && cx >= lcx && cx < lcx + TK_SPAN;
+    const bool part = !done && cy == lcy && cz == lcz && cx >= lcx && cx < lcx + span_lim;
     const int hix = __reduce_max_sync(0xffffffffu, part ? cx : lcx);
     const int xa = lcx - 1, xb = hix + 1;                       // scanned cell range in x
     const int x0 = max(xa, 0), x1 = min(xb, G.nx - 1);
-    // ---- the nine rows of the tile: bounds (lanes 0..8), offsets, staging
+    // ---- the nine rows of the tile: bounds (lanes 0..8), staging
     int s = 0, e = 0;
     if (lane < 9) {
       const int z = lcz + lane / 3 - 1, y = lcy + lane % 3 - 1;
@@ -116,120 +243,147 @@ __global__ void __launch_bounds__(32 * TK_WARPS) k_knn_tile(SearchArgs a, const 
         s = __ldg(&cs[row + x0]); e = __ldg(&cs[row + x1 + 1]);
       }
     }
-    const int ps = s >> 1;
-    const int np = e > s ? ((e + 1) >> 1) - ps : 0;
-    int off = np;
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += v; }
-    const int total = __shfl_sync(0xffffffffu, off, 15);
-    off -= np;
-    const bool fits = total <= TK_CAP_PAIRS;
+    const int npad = stage_rows(wt, ta.pairs, lane, s, e);
+    if (npad < 0 && hix > lcx) { span_lim = max(1, (hix - lcx + 1) >> 1); continue; }   // too many candidates: narrower tile
+    span_lim = TK_SPAN;
     bool final_ok = false;
     Top5 tt;
     top5_init(tt);
-    if (fits && total > 0) {
-      fence_proxy_async();              // earlier generic-proxy accesses of this buffer (previous tile) before the async writes
-      __syncwarp();
-      if (lane == 0) mbar_expect_tx(bar, (unsigned)total * 32u);
-      __syncwarp();
-      if (np > 0) bulk_g2s(tile + off, gpairs + ps, (unsigned)np * 32u, bar);
-      mbar_wait(bar, parity);
-      parity ^= 1u;
-      // the pair run of a row may start / end with a half-record of the neighbouring cell: neutralise it
-      if (np > 0) {
-        if (s & 1) { tile[off].x0 = PAIR_FAR; tile[off].i0 = 0x7fffffff; }
-        if (e & 1) { tile[off + np - 1].x1 = PAIR_FAR; tile[off + np - 1].i1 = 0x7fffffff; }
-      }
-      const int npad = (total + 7) & ~7;
-      if (lane < npad - total) {
-        PairRec f; f.x0 = PAIR_FAR; f.x1 = PAIR_FAR; f.y0 = 0.f; f.y1 = 0.f; f.z0 = 0.f; f.z1 = 0.f; f.i0 = 0x7fffffff; f.i1 = 0x7fffffff;
-        tile[total + lane] = f;
-      }
-      __syncwarp();
-      if (part) {
-        const ulonglong2* T2 = reinterpret_cast<const ulonglong2*>(tile);
-        // ---- pass A: eight interleaved running minima of the packed distances
-        float m0 = INF, m1 = INF, m2 = INF, m3 = INF, m4 = INF, m5 = INF, m6 = INF, m7 = INF;
+    if (npad > 0 && part) {
+      const ulonglong2* T2 = reinterpret_cast<const ulonglong2*>(wt.tile);
+      // ---- pass A: eight interleaved running minima of the packed distances
+      float m0 = INF, m1 = INF, m2 = INF, m3 = INF, m4 = INF, m5 = INF, m6 = INF, m7 = INF;
 #pragma unroll 1
-        for (int k = 0; k < npad; k += 4) {
-          float d[8];
+      for (int k = 0; k < npad; k += 4) {
+        float d[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const ulonglong2 xy = T2[2 * (k + u)];
-            const unsigned long long zz = *reinterpret_cast<const unsigned long long*>(&T2[2 * (k + u) + 1]);
-            const f32x2_t dx = sub2(qx2, xy.x), dy = sub2(qy2, xy.y), dz = sub2(qz2, zz);
-            unpack2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), d[2 * u], d[2 * u + 1]);
-          }
-          m0 = fminf(m0, d[0]); m1 = fminf(m1, d[1]); m2 = fminf(m2, d[2]); m3 = fminf(m3, d[3]);
-          m4 = fminf(m4, d[4]); m5 = fminf(m5, d[5]); m6 = fminf(m6, d[6]); m7 = fminf(m7, d[7]);
-        }
-        // five distinct candidates lie within the 5th smallest minimum: an upper bound of the exact 5th distance once the
-        // fused packed arithmetic (<= 4e-7 relative from the unfused order) is covered by the margin; nothing beyond the
-        // radius gate can matter (Estimator.cpp:3651)
-        const float bound = fminf(fifth_of_8(m0, m1, m2, m3, m4, m5, m6, m7) * TK_MARGIN, gate_cap);
-        const float thr = bound * TK_MARGIN;
-        // ---- pass B: packed distances again; a 16-bit survivor mask per word of 8 pair records, parked in shared memory
-        const int nwords = npad >> 3;
-#pragma unroll 1
-        for (int w = 0; w < nwords; ++w) {
-          unsigned m = 0;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const ulonglong2 xy = T2[2 * (8 * w + u)];
-            const unsigned long long zz = *reinterpret_cast<const unsigned long long*>(&T2[2 * (8 * w + u) + 1]);
-            const f32x2_t dx = sub2(qx2, xy.x), dy = sub2(qy2, xy.y), dz = sub2(qz2, zz);
-            float d0, d1;
-            unpack2(fma2(dz, dz, fma2(dy, dy, mul2(dx, dx))), d0, d1);
-            if (d0 <= thr) m |= 1u << (2 * u);
-            if (d1 <= thr) m |= 2u << (2 * u);
-          }
-          mask[w * 32] = (uint16_t)m;
-        }
-        {
-          // ---- flush: survivors re-evaluated with the exact distance, exact (distance, index) order
-          const float* tf = reinterpret_cast<const float*>(tile);
-#pragma unroll 1
-          for (int w = 0; w < nwords; ++w) {
-            unsigned m = mask[w * 32];
-            while (m) {
-              const int j = __ffs(m) - 1;
-              m &= m - 1;
-              const float* rec = tf + (8 * w + (j >> 1)) * 8 + (j & 1);
-              const int id = __float_as_int(rec[6]);
-              top5_push(tt, l2_simple(qx, qy, qz, rec[0], rec[2], rec[4]), id);
-            }
-          }
-          // distance to the faces of the scanned box; faces clipped by the grid are infinitely far (nothing lives outside)
-          float b = INF;
-          if (xa > 0)               b = fminf(b, qx - (G.ox + (float)xa * G.cell));
-          if (xb < G.nx - 1)        b = fminf(b, (G.ox + (float)(xb + 1) * G.cell) - qx);
-          if (lcy - 1 > 0)          b = fminf(b, qy - (G.oy + (float)(lcy - 1) * G.cell));
-          if (lcy + 1 < G.ny - 1)   b = fminf(b, (G.oy + (float)(lcy + 2) * G.cell) - qy);
-          if (lcz - 1 > 0)          b = fminf(b, qz - (G.oz + (float)(lcz - 1) * G.cell));
-          if (lcz + 1 < G.nz - 1)   b = fminf(b, (G.oz + (float)(lcz + 2) * G.cell) - qz);
-          const float bs = b * 0.999f - 2e-3f;   // safety: float rounding of cell assignment / face positions
-          final_ok = (b == INF) || (bs > 0.f && key_dist(tt.k4) <= bs * bs) || bs >= gate_r;
-        }
+        for (int u = 0; u < 4; ++u) pair_dist(T2, k + u, q.nqx2, q.nqy2, q.nqz2, d[2 * u], d[2 * u + 1]);
+        m0 = fminf(m0, d[0]); m1 = fminf(m1, d[1]); m2 = fminf(m2, d[2]); m3 = fminf(m3, d[3]);
+        m4 = fminf(m4, d[4]); m5 = fminf(m5, d[5]); m6 = fminf(m6, d[6]); m7 = fminf(m7, d[7]);
       }
+      // five distinct candidates lie within the 5th smallest minimum: an upper bound of the exact 5th distance once the
+      // fused packed arithmetic (<= 4e-7 relative from the unfused order) is covered by the margin; nothing beyond the
+      // radius gate can matter (Estimator.cpp:3651)
+      const float bound = fminf(fifth_of_8(m0, m1, m2, m3, m4, m5, m6, m7) * TK_MARGIN, gate_cap);
+      filter_and_flush(wt, npad, q, bound * TK_MARGIN, tt);
+      // distance to the faces of the scanned box; faces clipped by the grid are infinitely far (nothing lives outside)
+      float b = INF;
+      if (xa > 0)               b = fminf(b, qx - (G.ox + (float)xa * G.cell));
+      if (xb < G.nx - 1)        b = fminf(b, (G.ox + (float)(xb + 1) * G.cell) - qx);
+      if (lcy - 1 > 0)          b = fminf(b, qy - (G.oy + (float)(lcy - 1) * G.cell));
+      if (lcy + 1 < G.ny - 1)   b = fminf(b, (G.oy + (float)(lcy + 2) * G.cell) - qy);
+      if (lcz - 1 > 0)          b = fminf(b, qz - (G.oz + (float)(lcz - 1) * G.cell));
+      if (lcz + 1 < G.nz - 1)   b = fminf(b, (G.oz + (float)(lcz + 2) * G.cell) - qz);
+      const float bs = b * 0.999f - 2e-3f;   // safety: float rounding of cell assignment / face positions
+      final_ok = (b == INF) || (bs > 0.f && key_dist(tt.k4) <= bs * bs) || bs >= gate_r;
     }
     if (part) {
       done = true;
-      store_top5(a, p, tt);                       // the team pass reads the 5th distance as its search radius
-    }
-    const bool defer = part && !final_ok;
-    const unsigned dm = __ballot_sync(0xffffffffu, defer);
-    if (dm) {
-      unsigned int base = 0;
-      if (lane == 0) { base = atomicAdd(a.n_deferred, (unsigned int)__popc(dm)); n_def += __popc(dm); }
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (defer) a.deferred[base + __popc(dm & ((1u << lane) - 1u))] = (uint32_t)p;
+      store_top5(a, p, tt);                       // deferred lanes: the second pass reads the 5th distance as its search radius
+      deferred = !final_ok;
     }
   }
-  if (a.n_fallback && lane == 0 && n_def) atomicAdd(a.n_fallback, n_def);
+  const unsigned dm = __ballot_sync(0xffffffffu, deferred);
+  if (lane == 0) { ta.dmask[gw] = dm; ta.dcount[gw] = __popc(dm); }
+}
+
+// deferred queries in sorted order: warp w's lanes land at dpos[w] ...
+__global__ void __launch_bounds__(256) k_defer_scatter(TileArgs ta) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w == 0) { const unsigned nd = (unsigned)ta.dpos[ta.nwarps]; *ta.sa.n_deferred = nd; if (ta.sa.n_fallback) atomicAdd(ta.sa.n_fallback, (unsigned long long)nd); }
+  if (w >= ta.nwarps) return;
+  unsigned m = ta.dmask[w];
+  int o = ta.dpos[w];
+  while (m) { const int b = __ffs(m) - 1; m &= m - 1; ta.sa.deferred[o++] = (uint32_t)(w * 32 + b); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// second pass: tiles of deferred queries; a tile's box is the union of its lanes' search spheres
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * TK_WARPS) k_knn_tile2(TileArgs ta) {
+  extern __shared__ __align__(128) unsigned char tk_smem[];
+  const SearchArgs& a = ta.sa;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const GridDesc& G = a.grid;
+  const int* __restrict__ cs = G.cell_start;
+  const float gate_cap = a.gate_sq * TK_MARGIN;
+  const unsigned int nd = (unsigned int)ta.dpos[ta.nwarps];
+  const unsigned int nwarps = gridDim.x * TK_WARPS;
+  WarpTile wt = warp_tile_init(tk_smem, wid, lane);
+  const int BIG = 0x3fffffff;
+  for (unsigned int base = (blockIdx.x * TK_WARPS + wid) * 32u; base < nd; base += nwarps * 32u) {
+    const unsigned int item = base + lane;
+    const bool valid = item < nd;
+    int64_t p = 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f, T = 0.f;
+    if (valid) {
+      p = a.deferred[item];
+      const float4 q4 = a.pm[a.order[p]];
+      qx = q4.x; qy = q4.y; qz = q4.z;
+      T = fminf(a.knn_sqd[4 * a.Qt + p], gate_cap);       // exact 5th distance inside the first pass's box (a proven bound), or the gate
+    }
+    const QueryRegs q = make_query(qx, qy, qz);
+    const float r = sqrtf(T) * 1.001f + 2e-3f;            // margin: float rounding of the cell assignment
+    const int cx = cell_coord(qx, G.ox, G.inv_cell), cy = cell_coord(qy, G.oy, G.inv_cell), cz = cell_coord(qz, G.oz, G.inv_cell);
+    const int xlo = cell_coord(qx - r, G.ox, G.inv_cell), xhi = cell_coord(qx + r, G.ox, G.inv_cell);
+    const int ylo = cell_coord(qy - r, G.oy, G.inv_cell), yhi = cell_coord(qy + r, G.oy, G.inv_cell);
+    const int zlo = cell_coord(qz - r, G.oz, G.inv_cell), zhi = cell_coord(qz + r, G.oz, G.inv_cell);
+    const float thr = T * TK_MARGIN;
+    // a wide sphere would blow up the box of every lane sharing its tile: those queries go straight to the team pass
+    const bool wide = valid && r > TK_WIDE_CELLS * G.cell;
+    {
+      const unsigned wm = __ballot_sync(0xffffffffu, wide);
+      if (wm) {
+        unsigned int fb = 0;
+        if (lane == 0) fb = atomicAdd(ta.n_fb, (unsigned int)__popc(wm));
+        fb = __shfl_sync(0xffffffffu, fb, 0);
+        if (wide) ta.fb_list[fb + __popc(wm & ((1u << lane) - 1u))] = (uint32_t)p;
+      }
+    }
+    bool done = !valid || wide;
+    for (;;) {
+      const unsigned pending = __ballot_sync(0xffffffffu, !done);
+      if (!pending) break;
+      const int leader = __ffs(pending) - 1;
+      const int lcx = __shfl_sync(0xffffffffu, cx, leader), lcy = __shfl_sync(0xffffffffu, cy, leader), lcz = __shfl_sync(0xffffffffu, cz, leader);
+      const bool part = !done && cy == lcy && cz == lcz && cx >= lcx && cx < lcx + TK_SPAN2;
+      const int X0 = max(__reduce_min_sync(0xffffffffu, part ? xlo : BIG), 0), X1 = min(__reduce_max_sync(0xffffffffu, part ? xhi : -BIG), G.nx - 1);
+      const int Y0 = max(__reduce_min_sync(0xffffffffu, part ? ylo : BIG), 0), Y1 = min(__reduce_max_sync(0xffffffffu, part ? yhi : -BIG), G.ny - 1);
+      const int Z0 = max(__reduce_min_sync(0xffffffffu, part ? zlo : BIG), 0), Z1 = min(__reduce_max_sync(0xffffffffu, part ? zhi : -BIG), G.nz - 1);
+      const int nyr = Y1 - Y0 + 1;
+      const int nrows = (X0 <= X1 && nyr > 0 && Z1 >= Z0) ? nyr * (Z1 - Z0 + 1) : 0;
+      Top5 tt;
+      top5_init(tt);
+      bool overflow = false;
+      for (int g = 0; g < nrows; g += 9) {
+        int s = 0, e = 0;
+        if (lane < 9 && g + lane < nrows) {
+          const int ri = g + lane;
+          const int row = ((Z0 + ri / nyr) * G.ny + (Y0 + ri % nyr)) * G.nx;
+          s = __ldg(&cs[row + X0]); e = __ldg(&cs[row + X1 + 1]);
+        }
+        const int npad = stage_rows(wt, ta.pairs, lane, s, e);
+        if (npad < 0) { overflow = true; break; }
+        if (npad > 0 && part) filter_and_flush(wt, npad, q, thr, tt);
+        __syncwarp();
+      }
+      if (part) {
+        done = true;
+        if (!overflow) store_top5(a, p, tt);
+      }
+      const unsigned fm = __ballot_sync(0xffffffffu, part && overflow);
+      if (fm) {
+        unsigned int fb = 0;
+        if (lane == 0) fb = atomicAdd(ta.n_fb, (unsigned int)__popc(fm));
+        fb = __shfl_sync(0xffffffffu, fb, 0);
+        if (part) ta.fb_list[fb + __popc(fm & ((1u << lane) - 1u))] = (uint32_t)p;
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// team pass: 8 lanes per deferred query
+// team pass (fallback): 8 lanes per query
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
   const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, m), hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), m);
@@ -237,10 +391,10 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 }
 __device__ __forceinline__ unsigned long long kmin(unsigned long long x, unsigned long long y) { return x < y ? x : y; }
 
-__global__ void __launch_bounds__(128) k_knn_team(SearchArgs a) {
+__global__ void __launch_bounds__(128, 12) k_knn_team(SearchArgs a, const uint32_t* __restrict__ qlist, const unsigned int* __restrict__ n_list) {
   const int lane = threadIdx.x & 31, team = lane >> 3, tl = lane & 7;
   const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
-  const unsigned int nd = *a.n_deferred;
+  const unsigned int nd = *n_list;
   const GridDesc& G = a.grid;
   const int* __restrict__ cs = G.cell_start;
   const float gate_cap = a.gate_sq * TK_MARGIN;
@@ -250,10 +404,10 @@ __global__ void __launch_bounds__(128) k_knn_team(SearchArgs a) {
     int64_t p = 0;
     float qx = 0.f, qy = 0.f, qz = 0.f, T = 0.f;
     if (valid) {
-      p = a.deferred[item];
+      p = qlist[item];
       const float4 q4 = a.pm[a.order[p]];
       qx = q4.x; qy = q4.y; qz = q4.z;
-      T = fminf(a.knn_sqd[4 * a.Qt + p], gate_cap);      // the tile pass's 5th distance inside its box, or +inf
+      T = fminf(a.knn_sqd[4 * a.Qt + p], gate_cap);      // the first pass's 5th distance inside its box, or +inf
     }
     Top5 t;
     top5_init(t);
@@ -277,14 +431,20 @@ __global__ void __launch_bounds__(128) k_knn_team(SearchArgs a) {
         if (xl > xh) continue;
         const int row = (z * G.ny + y) * G.nx;
         const int s = __ldg(&cs[row + xl]), e = __ldg(&cs[row + xh + 1]);
-        for (int k = s; k < e; ++k) {
-          const float4 c = __ldg(&G.pts[k]);
-          const float d = l2_simple(qx, qy, qz, c.x, c.y, c.z);
-          if (d <= d4f) {
-            const unsigned long long key = make_key(d, __float_as_int(c.w));
-            if (key < t.k4) {
-              t.k4 = key; GLIO_KSWAP(t.k3, t.k4) GLIO_KSWAP(t.k2, t.k3) GLIO_KSWAP(t.k1, t.k2) GLIO_KSWAP(t.k0, t.k1)
-              d4f = fminf(d4f, key_dist(t.k4));
+        for (int k = s; k < e; k += 4) {
+          // four independent loads in flight per lane (the loop is latency-bound otherwise); the tail is padded with far fillers
+          float4 c[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) c[u] = (k + u < e) ? __ldg(&G.pts[k + u]) : make_float4(PAIR_FAR, 0.f, 0.f, __int_as_float(0x7fffffff));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float d = l2_simple(qx, qy, qz, c[u].x, c[u].y, c[u].z);
+            if (d <= d4f) {
+              const unsigned long long key = make_key(d, __float_as_int(c[u].w));
+              if (key < t.k4) {
+                t.k4 = key; GLIO_KSWAP(t.k3, t.k4) GLIO_KSWAP(t.k2, t.k3) GLIO_KSWAP(t.k1, t.k2) GLIO_KSWAP(t.k0, t.k1)
+                d4f = fminf(d4f, key_dist(t.k4));
+              }
             }
           }
         }
@@ -302,11 +462,29 @@ __global__ void __launch_bounds__(128) k_knn_team(SearchArgs a) {
   }
 }
 
-void knn_tile_run(const SearchArgs& sa, const PairRec* d_pairs, cudaStream_t st, LaunchCounter& lc) {
+void knn_tile_run(const SearchArgs& sa, const PairRec* d_pairs, DevBuf<int>& work, DevBuf<int>& scan_tmp, cudaStream_t st, LaunchCounter& lc) {
   GLIO_REQUIRE(d_pairs != nullptr, GLIO_ERR_STATE, "knn_tile_run: the grid has no pair layout (build_pairs)");
+  static bool attr_done = false;
+  if (!attr_done) {
+    GLIO_CUDA_TRY(cudaFuncSetAttribute(k_knn_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, TK_SMEM));
+    GLIO_CUDA_TRY(cudaFuncSetAttribute(k_knn_tile2, cudaFuncAttributeMaxDynamicSharedMemorySize, TK_SMEM));
+    attr_done = true;
+  }
   const unsigned nb = (unsigned)((sa.Qt + 32 * TK_WARPS - 1) / (32 * TK_WARPS));
-  lc.begin("k_knn_tile", st); k_knn_tile<<<nb, 32 * TK_WARPS, 0, st>>>(sa, d_pairs); lc.end(st);
-  lc.begin("k_knn_team", st); k_knn_team<<<148 * 8, 128, 0, st>>>(sa); lc.end(st);
+  const int nw = (int)nb * TK_WARPS;
+  // work layout: dmask[nw] | dcount[nw + 1] | dpos[nw + 1] | n_fb
+  work.reserve((size_t)3 * nw + 8);
+  TileArgs ta;
+  ta.sa = sa; ta.pairs = d_pairs; ta.nwarps = nw;
+  ta.dmask = reinterpret_cast<unsigned int*>(work.p); ta.dcount = work.p + nw; ta.dpos = work.p + 2 * nw + 1;
+  ta.n_fb = reinterpret_cast<unsigned int*>(work.p + 3 * nw + 2); ta.fb_list = sa.deferred + sa.Qt;     // second half of the 2*Qt list buffer
+  GLIO_CUDA_TRY(cudaMemsetAsync(ta.dcount + nw, 0, sizeof(int), st));
+  GLIO_CUDA_TRY(cudaMemsetAsync(ta.n_fb, 0, sizeof(unsigned int), st));
+  lc.begin("k_knn_tile", st); k_knn_tile<<<nb, 32 * TK_WARPS, TK_SMEM, st>>>(ta); lc.end(st);
+  exclusive_scan_i32(ta.dcount, work.p + 2 * nw + 1, (int64_t)nw + 1, scan_tmp, st, lc);
+  lc.begin("k_defer_scatter", st); k_defer_scatter<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(ta); lc.end(st);
+  lc.begin("k_knn_tile2", st); k_knn_tile2<<<148 * 4, 32 * TK_WARPS, TK_SMEM, st>>>(ta); lc.end(st);
+  lc.begin("k_knn_team", st); k_knn_team<<<148 * 4, 128, 0, st>>>(sa, ta.fb_list, ta.n_fb); lc.end(st);
   GLIO_CUDA_TRY(cudaGetLastError());
 }
 

@@ -33,5 +33,5 @@ for ppc, mode in cfgs:
     same = dig == ref[0] and np.array_equal(nm, ref[1])
     line = " ".join("%s=%.3f" % (k.replace("k_", ""), v[0] / v[1]) for k, v in prof.items() if k.startswith("k_knn") or k.startswith("k_plane") or k in ("k_transform_hist", "k_order_scatter"))
     knn = sum(v[0] / v[1] for k, v in prof.items() if k.startswith("k_knn"))
-    print("mode=%s ppc=%s knn_total=%.3f ms exact=%s | %s" % (mode, ppc, knn, same, line), flush=True)
+    print("mode=%s ppc=%s knn_total=%.3f ms exact=%s deferred=%d | %s" % (mode, ppc, knn, same, nfb, line), flush=True)
     ctx.close()

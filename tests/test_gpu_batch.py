@@ -165,3 +165,27 @@ def test_uploaded_pair_matches_equal_associated_ones(setup):
         assert abs(g2["cost"] - g1["cost"]) <= 1e-13 * g1["cost"]
     finally:
         c2.close()
+
+
+def test_pair_association_at_cfg3_scan_size(oracle):
+    """One scan-to-multiscan pair at the BASELINE cfg 3 / cfg 4 scan size (Q = 100 k points per keyframe, Estimator.cpp:3710-3806):
+    the compacted match list, weights and local-frame normal / centroid bit-exact against the oracle (kd-tree over the searched
+    frame, all host threads)."""
+    from glio_b200 import api
+    B = synth.batch_problem(K=13, Q=100_000, seed=synth.SEED0 + 3, search_range=6, frames=[5, 8])
+    ctx = api.Context(0)
+    try:
+        for k in (5, 8):
+            ctx.batch_set_frame(k, B["scans"][k], B["poses_init"][k])
+        nm = ctx.batch_associate_pairs([5, 8], [8, 5])
+        for i, (c, o) in enumerate(((5, 8), (8, 5))):
+            ro = oracle.assoc_pair(B["scans"][c], B["poses_init"][c, :3], B["poses_init"][c, 3:], B["scans"][o],
+                                   B["poses_init"][o, :3], B["poses_init"][o, 3:])
+            m = ctx.batch_get_matches(c, o, 100_000)
+            v = ro["status"] == oracle.GO_VALID
+            assert m["n"] == nm[i] == ro["nvalid"] == int(v.sum()) and m["n"] > 50_000
+            assert np.array_equal(m["src"], np.nonzero(v)[0].astype(np.int32))
+            assert np.array_equal(m["weight"], ro["weight"][v])
+            assert np.array_equal(m["normal_cent"], ro["normal_cent"][v])
+    finally:
+        ctx.close()

@@ -21,10 +21,11 @@ def big(oracle):
 
 
 def test_full_size_association_matches_oracle_on_whole_scans(big, oracle):
-    """Two complete 100k-point scans against the 1M-point map: every query bit-exact vs the oracle (kd-tree search)."""
+    """All 20 complete 100k-point scans of the cfg-2 window against the 1M-point map: every one of the 2 M queries bit-exact vs
+    the oracle (kd-tree search, all host threads)."""
     ctx, P, nm = big
     tree = oracle.KdTree(P["map_xyz"])
-    for k in (0, 13):
+    for k in range(20):
         t2, q2 = ctx.lidar_pose(P["poses_init"][k])
         o = oracle.assoc_scan_to_map(P["map_xyz"], P["scans"][k], t2, q2, tree=tree)
         d = ctx.get_assoc_debug(k, 100_000)
@@ -85,6 +86,31 @@ def test_full_size_properties(big, oracle):
     assert np.max(np.abs(full["H"][k] - o["H"])) <= 1e-11 * np.max(np.abs(o["H"]))
     assert np.max(np.abs(full["g"][k] - o["g"])) <= 1e-11 * np.max(np.abs(o["g"]))
     assert full["cost"][k] == pytest.approx(o["cost_total"], rel=1e-12)
+
+
+def test_full_size_solve_matches_oracle(big, oracle):
+    """The cfg-2 solve (2 M residuals, 20 keyframes) against the oracle's literal Ceres loop on the same matches: same number of
+    iterations, every accepted/rejected decision, per-iteration tangent update <= 1e-6 m / 1e-8 rad, final poses."""
+    ctx, P, nm = big
+    tree = oracle.KdTree(P["map_xyz"])
+    prob = oracle.WindowProblem(P["poses_init"], None, P["q_lb"], P["t_lb"], huber_delta=1.0)
+    for k in range(20):
+        t2, q2 = ctx.lidar_pose(P["poses_init"][k])
+        o = oracle.assoc_scan_to_map(P["map_xyz"], P["scans"][k], t2, q2, tree=tree)
+        v = o["status"] == oracle.GO_VALID
+        prob.add_unary(np.full(int(v.sum()), k, np.int32), P["scans"][k][v], o["nsd"][v], o["score"][v])
+    import os
+    ro = prob.solve(oracle.solver_options(), mode=0, nthreads=os.cpu_count() or 1)
+    rg = ctx.window_solve(P["poses_init"])
+    assert rg["summary"].num_iterations == ro["summary"].num_iterations >= 3
+    assert len(rg["steps"]) == len(ro["steps"])
+    for a, b in zip(rg["steps"], ro["steps"]):
+        a = a.reshape(20, 6); b = b.reshape(20, 6)
+        assert np.max(np.abs(a[:, :3] - b[:, :3])) <= 1e-6 and np.max(2 * np.linalg.norm(a[:, 3:] - b[:, 3:], axis=1)) <= 1e-8
+    for ig, io in zip(rg["iterations"], ro["iterations"]):
+        assert ig["step_is_successful"] == io["step_is_successful"] and ig["step_is_valid"] == io["step_is_valid"]
+        assert ig["cost"] == pytest.approx(io["cost"], rel=1e-9)
+    assert np.max(np.abs(rg["poses"][:, :3] - ro["poses"][:, :3])) <= 1e-6 and np.max(np.abs(rg["poses"][:, 3:] - ro["poses"][:, 3:])) <= 1e-8
 
 
 def test_full_size_solve_decreases_cost_and_is_deterministic(big):

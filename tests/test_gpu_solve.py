@@ -104,9 +104,26 @@ def test_front_end_scan_matcher_settings(oracle):
         ge = ctx.eval_unary(state)
         assert np.max(np.abs(ge["H"][0] - oe["H"])) <= 1e-11 * np.max(np.abs(oe["H"]))
         assert np.max(np.abs(ge["g"][0] - oe["g"])) <= 1e-11 * np.max(np.abs(oe["g"])) and abs(ge["cost"][0] - oe["cost_total"]) <= 1e-11 * oe["cost_total"]
-        # one Ceres solve of the front end's loop (6-dof, LiDAR residuals only)
+        # one Ceres solve of the front end's loop (6-dof, LiDAR residuals only) with the front end's own options
+        # (LidarOdometry.cpp:521-530): trust_region_strategy_type = LEVENBERG_MARQUARDT (Ceres' default), DENSE_QR, at most
+        # 4 iterations.  Oracle: LM over an unpivoted Householder QR of [J; D] (reserved = 2); product: LM over the normal equations.
         prob = oracle.WindowProblem(state, None, ident_q, zero_t, huber_delta=0.1)
         prob.add_unary(kf, P["scans"][0][v], o["nsd"][v], ones)
+        for max_it in (4, 15):
+            prob.reset_state(state)
+            ro = prob.solve(oracle.solver_options(reserved=2, max_num_iterations=max_it), mode=0)
+            rg = ctx.window_solve(state, None, None, api.default_solver_options(trust_region_strategy=1, max_num_iterations=max_it))
+            assert rg["summary"].num_iterations == ro["summary"].num_iterations >= 2
+            assert len(rg["steps"]) == len(ro["steps"])
+            for a, b in zip(rg["steps"], ro["steps"]):
+                assert np.max(np.abs(a[:3] - b[:3])) <= 1e-6 and np.max(np.abs(a[3:6] - b[3:6])) <= 1e-8
+            for ig, io in zip(rg["iterations"], ro["iterations"]):
+                assert ig["step_is_successful"] == io["step_is_successful"] and ig["step_is_valid"] == io["step_is_valid"]
+                assert ig["trust_region_radius"] == pytest.approx(io["trust_region_radius"], rel=1e-7)
+            assert np.max(np.abs(rg["poses"] - ro["poses"])) <= 1e-6
+            assert rg["summary"].final_cost < 0.7 * rg["summary"].initial_cost
+        # and the dogleg solve still agrees as before (the Estimator's strategy on the same problem)
+        prob.reset_state(state)
         ro = prob.solve(oracle.solver_options(), mode=0)
         rg = ctx.window_solve(state, None, None, api.default_solver_options())
         assert rg["summary"].num_iterations == ro["summary"].num_iterations >= 2

@@ -109,3 +109,39 @@ def test_plane_unit_normal_matches_lapack_on_synthetic_neighbourhoods(oracle):
         n_ref, d_ref = x / nrm, 1.0 / nrm
         scale = 1e-13 * np.linalg.cond(A) + 1e-12
         assert np.max(np.abs(o["plane"][i, :3] - n_ref)) <= scale and abs(o["plane"][i, 3] - d_ref) <= scale * max(1.0, abs(d_ref))
+
+
+def test_oracle_lm_dense_qr_equals_lm_normal_equations(oracle):
+    """Levenberg-Marquardt in the oracle (ceres.tgz::internal/ceres/levenberg_marquardt_strategy.cc:69-160): the literal DENSE_QR
+    linear solve of [J; D] (the front end's options, LidarOdometry.cpp:521-530) and the normal-equation Cholesky solve give
+    the same iterates to rounding, the radius follows Ceres' rule, and the path differs from the dogleg one."""
+    P = synth.window_problem(W=1, Q=3000, M=40000, seed=synth.SEED0 + 9)
+    ident_q, zero_t = [1.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0]
+    t2, q2 = synth.lidar_pose_in_world(P["poses_init"][0, :3], P["poses_init"][0, 3:7])
+    state = np.concatenate([t2, q2])[None, :]
+    prm = oracle.default_params(); prm.kd_max_radius = 1.0; prm.surf_dist_thres = 0.06; prm.weight_min = 0.4; prm.lidar_const = 1.0
+    o = oracle.assoc_scan_to_map(P["map_xyz"], P["scans"][0], t2, q2, prm=prm)
+    v = o["status"] == oracle.GO_VALID
+    kf = np.zeros(int(v.sum()), np.int32); ones = np.ones(int(v.sum()))
+    prob = oracle.WindowProblem(state, None, ident_q, zero_t, huber_delta=0.1)
+    prob.add_unary(kf, P["scans"][0][v], o["nsd"][v], ones)
+    res = {}
+    for strat in (0, 1, 2):
+        prob.reset_state(state)
+        res[strat] = prob.solve(oracle.solver_options(reserved=strat, max_num_iterations=8), mode=0)
+    a, b = res[1], res[2]
+    assert a["summary"].num_iterations == b["summary"].num_iterations >= 3
+    for x, y in zip(a["steps"], b["steps"]):
+        assert np.max(np.abs(x - y)) <= 1e-9
+    for ia, ib in zip(a["iterations"], b["iterations"]):
+        assert ia["step_is_successful"] == ib["step_is_successful"]
+        assert ia["trust_region_radius"] == pytest.approx(ib["trust_region_radius"], rel=1e-8)
+    # Ceres' rule on the accepted steps: radius_{k+1} = min(max_radius, radius_k / max(1/3, 1 - (2 rho - 1)^3))
+    its = a["iterations"]
+    for prev, cur in zip(its, its[1:]):
+        if cur["step_is_successful"]:
+            want = min(1e16, prev["trust_region_radius"] / max(1.0 / 3.0, 1.0 - (2.0 * cur["relative_decrease"] - 1.0) ** 3))
+            assert cur["trust_region_radius"] == pytest.approx(want, rel=1e-12)
+    assert a["summary"].final_cost < 0.7 * a["summary"].initial_cost
+    # a different algorithm from the dogleg one: the first steps are not the same vector
+    assert np.max(np.abs(res[0]["steps"][0] - a["steps"][0])) > 1e-9
