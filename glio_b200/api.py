@@ -47,6 +47,9 @@ def lib():
         L.glio_launch_count.argtypes = [C.c_void_p]
         L.glio_destroy.argtypes = [C.c_void_p]
         L.glio_destroy.restype = None
+        L.glio_marg_prior_destroy.argtypes = [C.c_void_p]
+        L.glio_marg_prior_destroy.restype = None
+        L.glio_marg_prior_create.restype = C.c_void_p
         _LIB = L
     return _LIB
 
@@ -213,6 +216,16 @@ class Context:
         assert len(strides) == 1 and len(mems) == 1
         self._chk(self._lib.glio_window_set_scans(self._h, C.c_int(W), ptrs, Q, C.c_int(strides.pop()), C.c_int(mems.pop())))
 
+    def window_set_scan(self, slot, scan):
+        keep, p, n, stride, mem = _points_arg(scan)
+        if not hasattr(self, "_slot_keep"):
+            self._slot_keep = {}
+        self._slot_keep[slot] = keep
+        self._chk(self._lib.glio_window_set_scan(self._h, C.c_int(slot), p, C.c_int64(n), C.c_int(stride), C.c_int(mem)))
+
+    def window_slide(self, W):
+        self._chk(self._lib.glio_window_slide(self._h, C.c_int(W)))
+
     def window_associate(self, poses_body):
         pb = np.ascontiguousarray(poses_body, np.float64).reshape(-1, 7)
         W = len(pb)
@@ -327,6 +340,25 @@ class HostFactorSet:
         a = [np.ascontiguousarray(v, np.float64) for v in (lever, sat)]
         self._lib.glio_hf_add_range(self._h, C.c_int(kf), _ptr(a[0]), _ptr(a[1]), C.c_double(rho), C.c_double(w))
 
+    def set_marg_prior(self, prior):
+        """Attach a MargPrior (or None) to this factor set: it then acts as the MarginalizationFactor of the window."""
+        self._prior_keep = prior
+        rc = self._lib.glio_hf_set_marg_prior(self._h, prior._h if prior is not None else None)
+        assert rc == 0
+
+    def marg_half_bandwidth(self):
+        return int(self._lib.glio_hf_marg_half_bandwidth(self._h))
+
+    def marg_evaluate(self, poses, speed_bias):
+        """The non-LiDAR part of MarginalizationInfo's A, b (marginalisation ordering, N = 6W + 18)."""
+        pb = np.ascontiguousarray(poses, np.float64).reshape(-1, 7); W = len(pb)
+        sb = np.ascontiguousarray(speed_bias, np.float64).reshape(W, 9)
+        N = 6 * W + 18
+        A = np.zeros((N, N)); b = np.zeros(N)
+        rc = self._lib.glio_hf_marg_evaluate(self._h, C.c_int(W), _ptr(pb), _ptr(sb), _ptr(A), _ptr(b))
+        assert rc == 0
+        return A, b
+
     def evaluate(self, poses, speed_bias=None, want_jac=True):
         pb = np.ascontiguousarray(poses, np.float64).reshape(-1, 7); W = len(pb)
         sb = None if speed_bias is None else np.ascontiguousarray(speed_bias, np.float64).reshape(W, 9)
@@ -346,6 +378,57 @@ class HostFactorSet:
                 self._lib.glio_hf_destroy(self._h); self._h = None
         except Exception:
             pass
+
+
+HOST_MARG_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
+class MargPrior:
+    """glio_marg_prior: linearized_jacobians / residuals + keep_block_data of MarginalizationInfo (next window's numbering)."""
+
+    def __init__(self, handle, lib_):
+        self._h = handle; self._lib = lib_
+        n = C.c_int(0); W = C.c_int(0)
+        self._lib.glio_marg_prior_size(self._h, C.byref(n), C.byref(W))
+        self.n, self.W = n.value, W.value
+
+    @classmethod
+    def from_arrays(cls, W, lin_jac, lin_res, x0_pose, x0_sb):
+        L = lib()
+        a = [np.ascontiguousarray(v, np.float64) for v in (lin_jac, lin_res, x0_pose, x0_sb)]
+        h = L.glio_marg_prior_create(C.c_int(W), _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]))
+        assert h
+        return cls(C.c_void_p(h), L)
+
+    def arrays(self):
+        n, W = self.n, self.W
+        out = dict(W=W, lin_jac=np.zeros((n, n)), lin_res=np.zeros(n), x0_pose=np.zeros((W - 1, 7)), x0_sb=np.zeros(9), A_info=np.zeros((n, n)), b_info=np.zeros(n))
+        self._lib.glio_marg_prior_get(self._h, _ptr(out["lin_jac"]), _ptr(out["lin_res"]), _ptr(out["x0_pose"]), _ptr(out["x0_sb"]), _ptr(out["A_info"]), _ptr(out["b_info"]))
+        return out
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.glio_marg_prior_destroy(self._h); self._h = None
+        except Exception:
+            pass
+
+
+def _window_marginalize(self, poses, speed_bias, host_factors=None, eps=1e-8):
+    """MarginalizationInfo::PreMarginalize + Marginalize of KF0 (Estimator.cpp:2462-2608): LiDAR blocks from the device, the
+    other factors from `host_factors` (a HostFactorSet).  Returns a MargPrior for the next window."""
+    pb = np.ascontiguousarray(poses, np.float64).reshape(-1, 7); W = len(pb)
+    sb = np.ascontiguousarray(speed_bias, np.float64).reshape(W, 9)
+    if host_factors is None:
+        fn, user = C.cast(None, HOST_MARG_FN), None
+    else:
+        fn, user = C.cast(self._lib.glio_hf_marg_evaluate, HOST_MARG_FN), host_factors._h
+    out = C.c_void_p()
+    self._chk(self._lib.glio_window_marginalize(self._h, C.c_int(W), _ptr(pb), _ptr(sb), fn, user, C.c_double(eps), C.byref(out)))
+    return MargPrior(out, self._lib)
+
+
+Context.window_marginalize = _window_marginalize
 
 
 def _window_solve(self, poses, speed_bias=None, host_factors=None, options=None, max_log=64, band=None):

@@ -440,7 +440,8 @@ struct FitArgs {
   const int32_t* knn_idx;
   const float* knn_sqd;
   AssocGates gates;
-  const float4* pts_by_idx;   // searched cloud, original order (x,y,z,idx)
+  const float4* pts_sorted;   // searched cloud, cell-sorted (x,y,z,idx): neighbouring queries gather neighbouring lines
+  const int* sorted_pos;      // original index -> position in pts_sorted (4 B per point: stays in L2)
   const float* oth_local;     // pair mode: local-frame points of the searched frame (original order)
   int oth_stride;
   uint8_t* status;
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(128, GLIO_FIT_MINBLOCKS) k_plane_fit(FitArgs a
     double A[3][5];
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
-      const float4 m = __ldg(&a.pts_by_idx[id[j]]);
+      const float4 m = __ldg(&a.pts_sorted[__ldg(&a.sorted_pos[id[j]])]);
       A[0][j] = (double)m.x; A[1][j] = (double)m.y; A[2][j] = (double)m.z;
     }
     double Aw[3][5];
@@ -555,7 +556,7 @@ void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const Assoc
   lc.begin("k_order_scatter", st); k_order_scatter<<<nb, 256, 0, st>>>(grid, Qt, w.pm, cell_pos.p, cell_count.p, w.order); lc.end(st);
   SearchArgs sa;
   sa.grid = grid; sa.Qt = Qt; sa.pm = w.pm; sa.order = w.order; sa.gate_sq = (float)gates.max_radius;
-  sa.knn_idx = w.knn_idx; sa.knn_sqd = w.knn_sqd; sa.n_fallback = w.n_fallback;
+  sa.knn_idx = w.knn_idx; sa.knn_sqd = w.knn_sqd; sa.n_fallback = w.n_fallback; sa.store_all_sqd = w.idx5 != nullptr;
   sa.tile_rings = w.tile_rings; sa.deferred = w.deferred; sa.n_deferred = w.n_deferred;
   GLIO_CUDA_TRY(cudaMemsetAsync(w.n_deferred, 0, sizeof(unsigned int), st));
   const unsigned ns = (unsigned)((Qt + 32 * KNN_WARPS - 1) / (32 * KNN_WARPS));
@@ -574,7 +575,7 @@ void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const Assoc
   }
   FitArgs fa;
   fa.Qt = Qt; fa.pm = w.pm; fa.order = w.order; fa.knn_idx = w.knn_idx; fa.knn_sqd = w.knn_sqd; fa.gates = gates;
-  fa.pts_by_idx = gb.tmp4.p; fa.oth_local = oth_local; fa.oth_stride = oth_stride;
+  fa.pts_sorted = gb.pts.p; fa.sorted_pos = gb.sorted_pos.p; fa.oth_local = oth_local; fa.oth_stride = oth_stride;
   fa.status = w.status; fa.nsd = w.nsd; fa.weight = w.weight; fa.normal_cent = w.normal_cent;
   fa.idx5 = w.idx5; fa.sqd5 = w.sqd5; fa.plane = w.plane;
   const unsigned nk = (unsigned)((Qt + 127) / 128);

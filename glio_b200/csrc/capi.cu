@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "hostmath.h"
 #include "solver.h"
+#include "marg.h"
 
 using namespace glio;
 
@@ -100,6 +101,8 @@ struct glio_ctx {
   PinnedBuf<int> h_counts;
   DevBuf<int> d_bad;
   DevBuf<int32_t> d_keep;
+  // K2e scratch (kept in the context: no cudaMalloc / cudaFree per call, nothing to leak when a call throws)
+  DevBuf<EdgeItem> e_items; DevBuf<int> e_start; DevBuf<double> e_part, e_out, e_poses;
 
   // evaluation
   DevBuf<EvalItem> d_items;
@@ -420,6 +423,10 @@ void glio_destroy(glio_ctx* c) {
   c->h_counts.release(); c->d_bad.release(); c->d_keep.release(); c->d_items.release(); c->d_kf_item_start.release();
   c->d_partials.release(); c->d_out.release(); c->d_poses.release(); c->d_r.release(); c->d_J.release(); c->h_out.release();
   c->h_poses.release(); c->h_flag.release(); c->d_ticket.release(); c->w_knn_idx.release(); c->w_knn_sqd.release(); c->d_stats.release(); c->w_deferred.release();
+  c->e_items.release(); c->e_start.release(); c->e_part.release(); c->e_out.release(); c->e_poses.release();
+  for (auto& r : c->lc.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& e : c->lc.pool) cudaEventDestroy(e);
+  c->lc.recs.clear(); c->lc.pool.clear();
   if (c->ev_scans) cudaEventDestroy(c->ev_scans);
   if (c->ev_main) cudaEventDestroy(c->ev_main);
   if (c->st_copy) cudaStreamDestroy(c->st_copy);
@@ -537,6 +544,8 @@ int glio_localmap_clear(glio_ctx* c) {
     GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
     for (auto& f : c->lm_frames) f->pts.release();
     c->lm_frames.clear();
+    for (auto& f : c->lm_spare) f->pts.release();
+    c->lm_spare.clear();
   });
 }
 
@@ -656,6 +665,43 @@ int glio_window_set_scans(glio_ctx* c, int W, const float* const* scans, const i
   });
 }
 
+// One keyframe's scan into one slot (copy stream for host buffers, like glio_window_set_scans): what a sliding window needs per
+// new keyframe - the other W-1 scans are already resident.
+int glio_window_set_scan(glio_ctx* c, int slot, const float* scan, int64_t Q, int stride, int mem) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(scan != nullptr && Q > 0, GLIO_ERR_ARG, "null or empty point array");
+    GLIO_REQUIRE(stride >= 3 && stride <= 64, GLIO_ERR_ARG, "stride_floats must be in [3,64]");
+    Slot& sl = c->slot(slot);
+    if (mem == GLIO_DEVICE) sl.scan_ptr = scan;
+    else {
+      GLIO_CUDA_TRY(cudaEventRecord(c->ev_main, c->st));
+      GLIO_CUDA_TRY(cudaStreamWaitEvent(c->st_copy, c->ev_main, 0));
+      sl.scan.reserve((size_t)Q * stride);
+      GLIO_CUDA_TRY(cudaMemcpyAsync(sl.scan.p, scan, (size_t)Q * stride * sizeof(float), cudaMemcpyHostToDevice, c->st_copy));
+      sl.scan_ptr = sl.scan.p;
+      GLIO_CUDA_TRY(cudaEventRecord(c->ev_scans, c->st_copy)); c->scans_pending = true;
+    }
+    sl.Q = Q; sl.stride = stride;
+  });
+}
+
+// slideWindow (GLIO/src/Estimator.cpp: the oldest keyframe leaves, every other one moves down one slot): O(1) per slot, no
+// copies; the matches of the slots move with them.  The new keyframe's scan then goes into slot W-1 with glio_window_set_scan.
+int glio_window_slide(glio_ctx* c, int W) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(W >= 2 && W <= 4096, GLIO_ERR_ARG, "bad window size");
+    c->slot(W - 1);
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st_copy));
+    std::unique_ptr<Slot> first = std::move(c->slots[0]);
+    for (int k = 0; k + 1 < W; ++k) c->slots[k] = std::move(c->slots[k + 1]);
+    c->slots[W - 1] = std::move(first);                       // its buffers are reused by the next upload
+    if (c->slots[W - 1]) { c->slots[W - 1]->Q = 0; c->slots[W - 1]->scan_ptr = nullptr; c->slots[W - 1]->n_match = 0; c->slots[W - 1]->n_sel = -1; }
+    c->items_dirty = true;
+  });
+}
+
 int glio_window_associate(glio_ctx* c, int W, const double* poses_body, int64_t* n_match) {
   if (!c) return GLIO_ERR_ARG;
   return guarded(c, [&] {
@@ -755,6 +801,34 @@ int glio_eval_unary(glio_ctx* c, int W, const double* poses_body, int jac_kind, 
   });
 }
 
+// ---- K3: marginalisation of KF0 (MarginalizationInfo::PreMarginalize + Marginalize, MarginalizationFactor.cpp:107-202)
+int glio_window_marginalize(glio_ctx* c, int W, const double* poses, const double* speed_bias, glio_host_marg_fn host_marg, void* user,
+                            double eps, glio_marg_prior** prior_out) {
+  if (!c || !prior_out) return GLIO_ERR_ARG;
+  *prior_out = nullptr;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(W >= 2 && W <= 4096 && poses && speed_bias, GLIO_ERR_ARG, "glio_window_marginalize: need W >= 2, poses and speed_bias");
+    const int N = 6 * W + 18, m = 15, n = N - m;
+    // LiDAR factors of every keyframe of the window with the ambient x,y,z quaternion columns (Estimator.cpp:2538-2576):
+    // device pass -> W x (21 upper-triangular H, 6 g, cost) in pinned host memory
+    eval_unary_blocks(c, W, poses, 1, true);
+    std::vector<double> A((size_t)N * N, 0.0), b(N, 0.0);
+    static const int ut[6][6] = {{0, 1, 2, 3, 4, 5}, {1, 6, 7, 8, 9, 10}, {2, 7, 11, 12, 13, 14}, {3, 8, 12, 15, 16, 17}, {4, 9, 13, 16, 18, 19}, {5, 10, 14, 17, 19, 20}};
+    for (int k = 0; k < W; ++k) {
+      const double* o = c->h_out.p + (size_t)k * GLIO_NACC;
+      const int base = marg_index_t(k);                       // t at base, q at base + 3 in every keyframe of this ordering
+      for (int p = 0; p < 6; ++p) { b[base + p] += o[21 + p]; for (int q = 0; q < 6; ++q) A[(size_t)(base + p) * N + base + q] += o[ut[p][q]]; }
+    }
+    if (host_marg) GLIO_REQUIRE(host_marg(user, W, poses, speed_bias, A.data(), b.data()) == 0, GLIO_ERR_STATE, "host_marg callback failed");
+    std::unique_ptr<glio_marg_prior> P(new glio_marg_prior());
+    std::vector<double> LJ((size_t)n * n), lr(n);
+    GLIO_REQUIRE(marginalize_dense(A.data(), b.data(), N, m, eps, LJ.data(), lr.data()) == GLIO_OK, GLIO_ERR_STATE, "marginalize_dense failed");
+    glio_marg_prior* made = glio_marg_prior_create(W, LJ.data(), lr.data(), poses + 7, speed_bias + 9);
+    GLIO_REQUIRE(made != nullptr, GLIO_ERR_STATE, "glio_marg_prior_create failed");
+    *prior_out = made;
+  });
+}
+
 void glio_default_solver_options(glio_solver_options* o) {
   if (!o) return;
   memset(o, 0, sizeof(*o));
@@ -836,12 +910,12 @@ static int window_solve_impl(glio_ctx* c, int W, double* poses, double* speed_bi
       add_device();
       if (hrc != 0) return false;
       if (want_jac) {
-        if (hb_fixed < 0) {
-          // the block structure of the problem is fixed, so the band of J^T J is too (window: prior + IMU chain + unary
-          // LiDAR blocks -> block tridiagonal); a dense coupling simply yields hb = n-1
+        // band of J^T J from what the callback actually wrote, re-derived at EVERY Jacobian evaluation (an entry that turns
+        // non-zero later must not be dropped); the LiDAR blocks need 5
+        {
           int w = 5;
           if (host_factors) for (int i = 0; i < n; ++i) for (int j = 0; j < i - w; ++j) if (Hd[(size_t)i * n + j] != 0.0 || Hd[(size_t)j * n + i] != 0.0) { w = i - j; break; }
-          hb_fixed = w;
+          hb_fixed = std::max(hb_fixed, w);
         }
         H->reset(n, hb_fixed);
         const int hb = H->hb;
@@ -1305,7 +1379,7 @@ int glio_eval_edge(glio_ctx* c, int W, const double* poses_body, double* H, doub
       }
     }
     start[W] = (int)items.size();
-    DevBuf<EdgeItem> d_items; DevBuf<int> d_start; DevBuf<double> d_part, d_out, d_poses;
+    DevBuf<EdgeItem>& d_items = c->e_items; DevBuf<int>& d_start = c->e_start; DevBuf<double>& d_part = c->e_part; DevBuf<double>& d_out = c->e_out; DevBuf<double>& d_poses = c->e_poses;
     d_items.reserve(items.size() + 1); d_start.reserve(W + 1); d_part.reserve((items.size() + 1) * GLIO_NACC); d_out.reserve((size_t)W * GLIO_NACC); d_poses.reserve((size_t)W * 7);
     if (!c->d_ticket.p) { c->d_ticket.reserve(1); GLIO_CUDA_TRY(cudaMemsetAsync(c->d_ticket.p, 0, sizeof(unsigned int), c->st)); }
     if (!items.empty()) GLIO_CUDA_TRY(cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(EdgeItem), cudaMemcpyHostToDevice, c->st));
@@ -1322,7 +1396,6 @@ int glio_eval_edge(glio_ctx* c, int W, const double* poses_body, double* H, doub
       if (g) for (int p = 0; p < 6; ++p) g[6 * k + p] = o[21 + p];
       if (cost) cost[k] = o[27];
     }
-    d_items.release(); d_start.release(); d_part.release(); d_out.release(); d_poses.release();
   });
 }
 

@@ -170,13 +170,14 @@ struct GridBuild {
   DevBuf<int> cell_start;
   DevBuf<float4> pts;
   DevBuf<float4> tmp4;     // unsorted (transformed) points, original order: (x,y,z,idx)
+  DevBuf<int> sorted_pos;  // original index -> position in pts (cell-sorted)
   DevBuf<PairRec> pairs;   // pair layout of pts (built when build_pairs; knn_mode 4)
   bool build_pairs = false;
   DevBuf<int> fill;        // scatter cursors
   DevBuf<int> scan_tmp;
   DevBuf<int> bounds;      // 6 order-preserving ints on device
   GridDesc desc{};
-  void release() { cell_start.release(); pts.release(); tmp4.release(); pairs.release(); fill.release(); scan_tmp.release(); bounds.release(); }
+  void release() { cell_start.release(); pts.release(); tmp4.release(); pairs.release(); sorted_pos.release(); fill.release(); scan_tmp.release(); bounds.release(); }
 };
 void grid_build(GridBuild& gb, const float* d_xyz, int stride, int64_t n, const double* t, const double* q,
                 float cell_size_hint, float pts_per_cell, cudaStream_t st, LaunchCounter& lc);

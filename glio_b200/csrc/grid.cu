@@ -156,12 +156,13 @@ __global__ void __launch_bounds__(256) k_cell_hist(const float4* __restrict__ pt
 
 __global__ void __launch_bounds__(256) k_cell_scatter(const float4* __restrict__ pts, int64_t n, GridDesc g,
                                                       const int* __restrict__ cell_start, int* __restrict__ fill,
-                                                      float4* __restrict__ sorted) {
+                                                      float4* __restrict__ sorted, int* __restrict__ sorted_pos) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float4 p = pts[i];
     int c = cell_of_clamped(g, p.x, p.y, p.z);
     int pos = cell_start[c] + atomicAdd(&fill[c], 1);
     sorted[pos] = p;
+    sorted_pos[i] = pos;          // original index -> position in the cell-sorted copy (K1b gathers neighbours from there)
   }
 }
 
@@ -183,6 +184,7 @@ void grid_build(GridBuild& gb, const float* d_xyz, int stride, int64_t n, const 
   GLIO_REQUIRE(n > 0 && n < (int64_t)1 << 31, GLIO_ERR_ARG, "grid_build: point count out of range");
   gb.tmp4.reserve((size_t)n);
   gb.pts.reserve((size_t)n);
+  gb.sorted_pos.reserve((size_t)n);
   gb.bounds.reserve(8);
   PoseD pose{};
   int has_pose = 0;
@@ -228,7 +230,7 @@ void grid_build(GridBuild& gb, const float* d_xyz, int stride, int64_t n, const 
   lc.begin("k_cell_hist", st); k_cell_hist<<<nb, 256, 0, st>>>(gb.tmp4.p, n, g, gb.fill.p); lc.end(st);
   exclusive_scan_i32(gb.fill.p, gb.cell_start.p, ncell + 1, gb.scan_tmp, st, lc);
   GLIO_CUDA_TRY(cudaMemsetAsync(gb.fill.p, 0, (size_t)(ncell + 1) * sizeof(int), st));
-  lc.begin("k_cell_scatter", st); k_cell_scatter<<<nb, 256, 0, st>>>(gb.tmp4.p, n, g, gb.cell_start.p, gb.fill.p, gb.pts.p); lc.end(st);
+  lc.begin("k_cell_scatter", st); k_cell_scatter<<<nb, 256, 0, st>>>(gb.tmp4.p, n, g, gb.cell_start.p, gb.fill.p, gb.pts.p, gb.sorted_pos.p); lc.end(st);
   if (gb.build_pairs) {
     gb.pairs.reserve((size_t)((n + 1) / 2 + 1));
     lc.begin("k_make_pairs", st); k_make_pairs<<<nb, 256, 0, st>>>(gb.pts.p, n, gb.pairs.p); lc.end(st);

@@ -56,7 +56,8 @@ struct SearchArgs {
   const uint32_t* order;
   float gate_sq;
   int32_t* knn_idx;     // [5][Qt] sorted order
-  float* knn_sqd;       // [5][Qt] sorted order
+  float* knn_sqd;       // [5][Qt] sorted order; rows 0..3 are written only when store_all_sqd (the gate needs the 5th only)
+  bool store_all_sqd;
   unsigned long long* n_fallback;   // statistics: queries deferred to the second pass
   int tile_rings;                   // (mode 0) rings the tile pass may scan before it defers a query
   uint32_t* deferred;               // sorted positions of deferred queries
@@ -66,8 +67,11 @@ struct SearchArgs {
 __device__ __forceinline__ void store_top5(const SearchArgs& a, int64_t p, const Top5& t) {
   a.knn_idx[0 * a.Qt + p] = key_idx(t.k0); a.knn_idx[1 * a.Qt + p] = key_idx(t.k1); a.knn_idx[2 * a.Qt + p] = key_idx(t.k2);
   a.knn_idx[3 * a.Qt + p] = key_idx(t.k3); a.knn_idx[4 * a.Qt + p] = key_idx(t.k4);
-  a.knn_sqd[0 * a.Qt + p] = key_dist(t.k0); a.knn_sqd[1 * a.Qt + p] = key_dist(t.k1); a.knn_sqd[2 * a.Qt + p] = key_dist(t.k2);
-  a.knn_sqd[3 * a.Qt + p] = key_dist(t.k3); a.knn_sqd[4 * a.Qt + p] = key_dist(t.k4);
+  a.knn_sqd[4 * a.Qt + p] = key_dist(t.k4);
+  if (a.store_all_sqd) {
+    a.knn_sqd[0 * a.Qt + p] = key_dist(t.k0); a.knn_sqd[1 * a.Qt + p] = key_dist(t.k1); a.knn_sqd[2 * a.Qt + p] = key_dist(t.k2);
+    a.knn_sqd[3 * a.Qt + p] = key_dist(t.k3);
+  }
 }
 
 // K1a, staged tile search + team pass (knn_tile.cu, GLIO_KNN_MODE=4)

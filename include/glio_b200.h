@@ -124,6 +124,12 @@ int glio_get_map(glio_ctx* ctx, int64_t capacity, float* xyz, int64_t* n_map);
 int glio_assoc_scan_to_map(glio_ctx* ctx, int slot, const float* scan_xyz, int64_t Q, int stride_floats, int mem,
                            const double t[3], const double q[4], int64_t* n_match);
 
+/* One keyframe's scan into one slot (host buffers travel on the copy stream; the next association waits for them), and the
+ * slide of the window by one keyframe (slideWindow in the reference: slot k+1 -> slot k, matches included; no copies).  A
+ * sliding window hands over ONE new scan per keyframe: the other W-1 stay resident. */
+int glio_window_set_scan(glio_ctx* ctx, int slot, const float* scan_xyz, int64_t Q, int stride_floats, int mem);
+int glio_window_slide(glio_ctx* ctx, int W);
+
 /* All W keyframes of the window in one launch (same results as W calls of glio_assoc_scan_to_map).
  * poses_body[W*7] are the keyframe (IMU-body) poses tmpTrans/tmpQuat; the lidar->map pose is formed on the
  * device-side host code exactly as Estimator.cpp:2216-2217 with params.q_lb/t_lb.
@@ -245,6 +251,32 @@ void glio_hf_add_between(glio_host_factor_set* s, int i, int j, const double dp[
                          const double sqrt_w[15]);
 void glio_hf_add_range(glio_host_factor_set* s, int kf, const double lever[3], const double sat[3], double rho, double w);
 int glio_hf_evaluate(void* user, int W, const double* poses, const double* speed_bias, int want_jac, double* H, double* g, double* cost);
+
+/* ---- K3: marginalisation of the oldest keyframe (MarginalizationInfo, GLIO/src/MarginalizationFactor.cpp:82-202; call site
+ * Estimator.cpp:2462-2608).  The reference re-evaluates EVERY LiDAR factor of the window (:2538-2576, one virtual Evaluate per
+ * residual) plus the IMU factor KF0->KF1 and the previous prior, accumulates the dense A = J^T J, b = J^T r with the ambient
+ * x,y,z quaternion columns (:9-17), removes KF0's 15 states by a Schur complement and factors the rest by an
+ * eigen-decomposition (:176-201).  glio_window_marginalize does the LiDAR part on the device (K2 with jac_kind = 1: one 6x6
+ * block + 6-vector per keyframe), asks the host callback for the other factors, and does the small dense algebra on the host.
+ * Orderings (see glio_b200/csrc/marg.h): marginalisation ordering N = 6W+18 = [KF0: t,q,sb | KF1: t,q,sb | KF k>=2: t,q];
+ * the prior keeps n = 6W+3 states, numbered as the NEXT window numbers them (addr_shift, Estimator.cpp:2583-2597).
+ * host_marg(user, W, poses, speed_bias, A[N*N], b[N]) ACCUMULATES the non-LiDAR factors (may be NULL). */
+typedef int (*glio_host_marg_fn)(void* user, int W, const double* poses, const double* speed_bias, double* A, double* b);
+typedef struct glio_marg_prior glio_marg_prior;
+int glio_window_marginalize(glio_ctx* ctx, int W, const double* poses, const double* speed_bias, glio_host_marg_fn host_marg, void* user,
+                            double eps /* 1e-8 in the reference */, glio_marg_prior** prior_out);
+glio_marg_prior* glio_marg_prior_create(int W, const double* lin_jac, const double* lin_res, const double* x0_poses, const double* x0_sb);
+void glio_marg_prior_destroy(glio_marg_prior* p);
+int glio_marg_prior_size(const glio_marg_prior* p, int* n, int* W);
+/* linearized_jacobians[n*n] row-major, linearized_residuals[n], keep_block_data (x0_poses[(W-1)*7], x0_sb[9]), and the
+ * information form A_info = J^T J [n*n], b_info = J^T r [n]; any pointer may be NULL */
+int glio_marg_prior_get(const glio_marg_prior* p, double* lin_jac, double* lin_res, double* x0_poses, double* x0_sb, double* A_info, double* b_info);
+/* stand-in host factors: attach the prior to the next window's factor set (it then takes part in glio_hf_evaluate[_band] as a
+ * MarginalizationFactor, MarginalizationFactor.cpp:232-330) and glio_hf_marg_evaluate = the glio_host_marg_fn of the set
+ * (previous prior + priors on KF0 + the between factor KF0->KF1). */
+int glio_hf_set_marg_prior(glio_host_factor_set* s, const glio_marg_prior* p /* copied; NULL removes */);
+int glio_hf_marg_evaluate(void* user, int W, const double* poses, const double* speed_bias, double* A, double* b);
+int glio_hf_marg_half_bandwidth(const glio_host_factor_set* s);
 
 /* ---- K1b: scan-to-multiscan (batch) association.
  * Replaces findGlobalCorrespondingSurfFeatures_Batch / ...Add_Batch (Estimator.cpp:3710-3892) and their driver

@@ -53,6 +53,9 @@ template <class T> void qconj(const T q[4], T o[4]) { o[0] = q[0]; o[1] = -q[1];
 struct Prior { int kf; double t0[3], q0[4], sb0[9], sw[15]; };
 struct Between { int i, j; double dp[3], dq[4], dv[3], dt, sw[15]; };
 struct Range { int kf; double lever[3], sat[3], rho, w; };
+// MarginalizationFactor (GLIO/src/MarginalizationFactor.cpp:222-330) of the previous window, numbered for THIS window:
+// kept blocks = KF0: t, q, speed-bias; KF k = 1..W-2: t, q   (n = 6W + 3 residuals); see glio_b200/csrc/marg.h for the order
+struct MargPrior { int W = 0, n = 0; std::vector<double> LJ, lr, x0_pose; double x0_sb[9]; };
 
 struct Opt {
   int32_t max_num_iterations, dogleg_type, use_nonmonotonic_steps, max_consecutive_nonmonotonic_steps;
@@ -74,6 +77,7 @@ struct Problem {
   // binary lidar (batch)
   std::vector<int32_t> bkc, bko; std::vector<float> bcp; std::vector<double> bnc, bscore;
   std::vector<Prior> priors; std::vector<Between> betweens; std::vector<Range> ranges;
+  MargPrior marg;
   // CRS jacobian
   std::vector<double> r; std::vector<int64_t> rowptr; std::vector<int32_t> col; std::vector<double> val;
   int64_t nrows = 0;
@@ -85,7 +89,7 @@ void quat_plus_jac(const double* x, double* P) { go_quat_plus_jacobian(x, P); }
 // number of rows / nnz layout is fixed for a problem: unary rows (6 nnz), prior rows 15 x nt, between 15 x 2nt, range 1 x 6
 void layout(Problem& P) {
   const int64_t N = (int64_t)P.kf.size(), NB = (int64_t)P.bkc.size();
-  P.nrows = N + NB + 15 * (int64_t)P.priors.size() + 15 * (int64_t)P.betweens.size() + (int64_t)P.ranges.size();
+  P.nrows = N + NB + 15 * (int64_t)P.priors.size() + 15 * (int64_t)P.betweens.size() + (int64_t)P.ranges.size() + (int64_t)P.marg.n;
   P.rowptr.assign(P.nrows + 1, 0);
   int64_t row = 0, nnz = 0;
   for (int64_t i = 0; i < N; ++i) { P.rowptr[row++] = nnz; nnz += 6; }
@@ -93,6 +97,7 @@ void layout(Problem& P) {
   for (size_t i = 0; i < P.priors.size(); ++i) for (int k = 0; k < 15; ++k) { P.rowptr[row++] = nnz; nnz += P.nt; }
   for (size_t i = 0; i < P.betweens.size(); ++i) for (int k = 0; k < 15; ++k) { P.rowptr[row++] = nnz; nnz += 2 * P.nt; }
   for (size_t i = 0; i < P.ranges.size(); ++i) { P.rowptr[row++] = nnz; nnz += 6; }
+  for (int i = 0; i < P.marg.n; ++i) { P.rowptr[row++] = nnz; nnz += P.nt + 6 * (P.marg.W - 2); }
   P.rowptr[row] = nnz;
   P.col.assign(nnz, 0); P.val.assign(nnz, 0.0); P.r.assign(P.nrows, 0.0);
 }
@@ -117,6 +122,43 @@ void finish_rows(Problem& P, const double* x, int nres, const Dual* res, int kfA
       if (P.has_sb) for (int c = 0; c < 9; ++c) { P.col[p] = P.nt * kf + 6 + c; P.val[p++] = dv[7 + c]; }
     }
   }
+}
+
+// MarginalizationFactor::Evaluate (MarginalizationFactor.cpp:232-330), literal: dx per kept block (quaternions: 2 vec of the
+// NORMALISED q0^-1 q, sign flipped when w < 0), residual = linearized_residuals + linearized_jacobians dx, and the analytic
+// ambient Jacobians the factor returns (quaternion block: +-2 J_cols Qleft(q0^-1).bottomRightCorner<3,4>(), which ignores the
+// normalisation).  Jamb[i] is n x 16 per keyframe slot: columns t(3) q(4: w,x,y,z) sb(9).
+struct MargEval { std::vector<double> res; std::vector<std::vector<double>> Jamb; };
+void marg_prior_eval(const Problem& P, const double* x, MargEval& E) {
+  const MargPrior& M = P.marg; const int n = M.n, W = M.W;
+  std::vector<double> dx(n, 0.0);
+  E.Jamb.assign(W - 1, std::vector<double>((size_t)n * 16, 0.0));
+  for (int k = 0; k <= W - 2; ++k) {
+    const double* xa = x + (size_t)P.na * k; const double* x0 = &M.x0_pose[(size_t)7 * k];
+    const int it = k == 0 ? 0 : 15 + 6 * (k - 1), iq = it + 3;
+    for (int c = 0; c < 3; ++c) dx[it + c] = xa[c] - x0[c];
+    // Quaterniond(x0).inverse() * Quaterniond(x)
+    const double n2 = x0[3] * x0[3] + x0[4] * x0[4] + x0[5] * x0[5] + x0[6] * x0[6];
+    const double qi[4] = {x0[3] / n2, -x0[4] / n2, -x0[5] / n2, -x0[6] / n2};
+    const double* q = xa + 3;
+    const double e[4] = {qi[0] * q[0] - qi[1] * q[1] - qi[2] * q[2] - qi[3] * q[3], qi[0] * q[1] + qi[1] * q[0] + qi[2] * q[3] - qi[3] * q[2],
+                         qi[0] * q[2] + qi[2] * q[0] + qi[3] * q[1] - qi[1] * q[3], qi[0] * q[3] + qi[3] * q[0] + qi[1] * q[2] - qi[2] * q[1]};
+    const double nrm = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2] + e[3] * e[3]);
+    const double sgn = e[0] < 0 ? -1.0 : 1.0;
+    for (int c = 0; c < 3; ++c) dx[iq + c] = sgn * 2.0 * e[1 + c] / nrm;
+    if (k == 0) for (int c = 0; c < 9; ++c) dx[6 + c] = (P.has_sb ? xa[7 + c] : M.x0_sb[c]) - M.x0_sb[c];
+    // Qleft(q0^-1).bottomRightCorner<3,4>() = [vec | w I + skew(vec)]
+    const double QL[3][4] = {{qi[1], qi[0], -qi[3], qi[2]}, {qi[2], qi[3], qi[0], -qi[1]}, {qi[3], -qi[2], qi[1], qi[0]}};
+    std::vector<double>& J = E.Jamb[k];
+    for (int r = 0; r < n; ++r) {
+      const double* lj = &M.LJ[(size_t)r * n];
+      for (int c = 0; c < 3; ++c) J[(size_t)r * 16 + c] = lj[it + c];
+      for (int c = 0; c < 4; ++c) { double a = 0; for (int m = 0; m < 3; ++m) a += lj[iq + m] * QL[m][c]; J[(size_t)r * 16 + 3 + c] = sgn * 2.0 * a; }
+      if (k == 0) for (int c = 0; c < 9; ++c) J[(size_t)r * 16 + 7 + c] = lj[6 + c];
+    }
+  }
+  E.res.assign(n, 0.0);
+  for (int r = 0; r < n; ++r) { double a = M.lr[r]; const double* lj = &M.LJ[(size_t)r * n]; for (int c = 0; c < n; ++c) a += lj[c] * dx[c]; E.res[r] = a; }
 }
 
 bool evaluate(Problem& P, const double* x, bool want_jac, double* cost_out) {
@@ -214,6 +256,25 @@ bool evaluate(Problem& P, const double* x, bool want_jac, double* cost_out) {
       for (int c = 0; c < 3; ++c) { double a = 0; for (int m = 0; m < 4; ++m) a += res[0].v[3 + m] * Pm[3 * m + c]; P.col[p] = P.nt * f.kf + 3 + c; P.val[p++] = a; }
     }
     row += 1;
+  }
+  // ---- marginalisation prior rows (no loss function: Estimator.cpp:2153-2158) ----
+  if (P.marg.n > 0) {
+    MargEval E; marg_prior_eval(P, x, E);
+    const int n = P.marg.n, W = P.marg.W;
+    double s2 = 0;
+    for (int r = 0; r < n; ++r) { P.r[row + r] = E.res[r]; s2 += E.res[r] * E.res[r]; }
+    cost += 0.5 * s2;
+    if (want_jac) for (int r = 0; r < n; ++r) {
+      int64_t p = P.rowptr[row + r];
+      for (int k = 0; k <= W - 2; ++k) {
+        const double* xa = x + (size_t)P.na * k; const double* dv = &E.Jamb[k][(size_t)r * 16];
+        double Pm[12]; quat_plus_jac(xa + 3, Pm);
+        for (int c = 0; c < 3; ++c) { P.col[p] = P.nt * k + c; P.val[p++] = dv[c]; }
+        for (int c = 0; c < 3; ++c) { double a = 0; for (int m = 0; m < 4; ++m) a += dv[3 + m] * Pm[3 * m + c]; P.col[p] = P.nt * k + 3 + c; P.val[p++] = a; }
+        if (k == 0 && P.has_sb) for (int c = 0; c < 9; ++c) { P.col[p] = P.nt * k + 6 + c; P.val[p++] = dv[7 + c]; }
+      }
+    }
+    row += n;
   }
   *cost_out = cost;
   return std::isfinite(cost);
@@ -349,6 +410,140 @@ void go_problem_host_normal_eq(void* h, double* H, double* g, double* cost) {
     for (int64_t q = Q.rowptr[i]; q < Q.rowptr[i + 1]; ++q) H[(size_t)Q.col[p] * n + Q.col[q]] += Q.val[p] * Q.val[q];
   }
   *cost = c;
+}
+
+void go_problem_set_marg_prior(void* h, int W, const double* lin_jac, const double* lin_res, const double* x0_pose, const double* x0_sb) {
+  Problem& P = *(Problem*)h; MargPrior& M = P.marg;
+  if (W <= 0 || !lin_jac) { M = MargPrior(); return; }
+  M.W = W; M.n = 6 * W + 3;
+  M.LJ.assign(lin_jac, lin_jac + (size_t)M.n * M.n); M.lr.assign(lin_res, lin_res + M.n);
+  M.x0_pose.assign(x0_pose, x0_pose + (size_t)(W - 1) * 7);
+  for (int c = 0; c < 9; ++c) M.x0_sb[c] = x0_sb ? x0_sb[c] : 0.0;
+}
+
+namespace {
+// cyclic Jacobi (the oracle's own eigen-solver: deliberately not the product's tridiagonal QL)
+void jacobi_eigh(std::vector<double> a, int n, std::vector<double>& w, std::vector<double>& V) {
+  V.assign((size_t)n * n, 0.0); for (int i = 0; i < n; ++i) V[(size_t)i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 80; ++sweep) {
+    double off = 0, dg = 0;
+    for (int i = 0; i < n; ++i) { dg += a[(size_t)i * n + i] * a[(size_t)i * n + i]; for (int j = i + 1; j < n; ++j) off += a[(size_t)i * n + j] * a[(size_t)i * n + j]; }
+    if (off <= 1e-32 * (dg + 1e-300)) break;
+    for (int p = 0; p < n - 1; ++p) for (int q = p + 1; q < n; ++q) {
+      const double apq = a[(size_t)p * n + q]; if (apq == 0.0) continue;
+      const double theta = (a[(size_t)q * n + q] - a[(size_t)p * n + p]) / (2.0 * apq);
+      const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0)), c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+      for (int k = 0; k < n; ++k) { const double x1 = a[(size_t)k * n + p], x2 = a[(size_t)k * n + q]; a[(size_t)k * n + p] = c * x1 - sn * x2; a[(size_t)k * n + q] = sn * x1 + c * x2; }
+      for (int k = 0; k < n; ++k) { const double x1 = a[(size_t)p * n + k], x2 = a[(size_t)q * n + k]; a[(size_t)p * n + k] = c * x1 - sn * x2; a[(size_t)q * n + k] = sn * x1 + c * x2; }
+      for (int k = 0; k < n; ++k) { const double x1 = V[(size_t)k * n + p], x2 = V[(size_t)k * n + q]; V[(size_t)k * n + p] = c * x1 - sn * x2; V[(size_t)k * n + q] = sn * x1 + c * x2; }
+    }
+  }
+  w.resize(n); for (int i = 0; i < n; ++i) w[i] = a[(size_t)i * n + i];
+}
+inline int marg_off(int kf) { return kf == 0 ? 0 : (kf == 1 ? 15 : 30 + 6 * (kf - 2)); }
+// ThreadsConstructA (MarginalizationFactor.cpp:3-29) for one residual block given ambient Jacobians in Dual slots of two keyframes
+void construct_A(int N, std::vector<double>& A, std::vector<double>& b, int nres, const Dual* res, int kfA, int kfB) {
+  const int kfs[2] = {kfA, kfB};
+  for (int r = 0; r < nres; ++r) {
+    int col[40]; double val[40]; int nz = 0;
+    for (int s = 0; s < 2; ++s) {
+      if (kfs[s] < 0) continue;
+      const double* dv = res[r].v + 16 * s; const int base = marg_off(kfs[s]);
+      for (int c = 0; c < 3; ++c) { col[nz] = base + c; val[nz++] = dv[c]; }
+      for (int c = 0; c < 3; ++c) { col[nz] = base + 3 + c; val[nz++] = dv[4 + c]; }      // rightCols(3) of the 4-wide quaternion Jacobian
+      if (kfs[s] <= 1) for (int c = 0; c < 9; ++c) { col[nz] = base + 6 + c; val[nz++] = dv[7 + c]; }
+    }
+    for (int i = 0; i < nz; ++i) { b[col[i]] += val[i] * res[r].a; for (int j = 0; j < nz; ++j) A[(size_t)col[i] * N + col[j]] += val[i] * val[j]; }
+  }
+}
+}  // namespace
+
+// MarginalizationInfo::PreMarginalize + Marginalize (MarginalizationFactor.cpp:107-202) over the factors the Estimator hands it
+// (Estimator.cpp:2464-2576): the previous prior, [stand-in priors on KF0], the IMU-like factor KF0 -> KF1, every LiDAR factor of
+// the window.  Requires speed/bias states.  Outputs in the prior ordering (next window's numbering).
+int go_problem_marginalize(void* h, double eps, int mode, double* lin_jac, double* lin_res, double* x0_pose, double* x0_sb, double* A_out, double* b_out) {
+  Problem& P = *(Problem*)h;
+  if (!P.has_sb || P.W < 2) return -1;
+  const int W = P.W, N = 6 * W + 18, m = 15, n = N - m;
+  const double* x = P.x.data();
+  std::vector<double> A((size_t)N * N, 0.0), b(N, 0.0);
+  // LiDAR factors: ambient x,y,z columns, Huber-corrected per ResidualBlockInfo::Evaluate (same corrector as Ceres')
+  {
+    std::vector<double> poses((size_t)W * 7), Hd((size_t)36 * W * W, 0.0), gd((size_t)6 * W, 0.0); double ct = 0;
+    for (int k = 0; k < W; ++k) for (int i = 0; i < 7; ++i) poses[7 * k + i] = x[(size_t)P.na * k + i];
+    const int64_t NL = (int64_t)P.kf.size();
+    if (NL > 0) go_eval_unary(mode, 1, W, poses.data(), P.q_lb, P.t_lb, P.huber, NL, P.kf.data(), P.cp.data(), P.nsd.data(), P.score.data(), nullptr, nullptr, nullptr, Hd.data(), gd.data(), &ct);
+    for (int k = 0; k < W; ++k) for (int p = 0; p < 6; ++p) { b[marg_off(k) + p] += gd[6 * k + p]; for (int q = 0; q < 6; ++q) A[(size_t)(marg_off(k) + p) * N + marg_off(k) + q] += Hd[(size_t)(6 * k + p) * 6 * W + 6 * k + q]; }
+  }
+  for (const Prior& f : P.priors) {
+    if (f.kf != 0) continue;
+    const double* xa = x;
+    Dual t[3] = {Dual(xa[0], 0), Dual(xa[1], 1), Dual(xa[2], 2)}, q[4] = {Dual(xa[3], 3), Dual(xa[4], 4), Dual(xa[5], 5), Dual(xa[6], 6)}, res[15];
+    for (int c = 0; c < 3; ++c) res[c] = Dual(f.sw[c]) * (t[c] - Dual(f.t0[c]));
+    Dual q0[4] = {Dual(f.q0[0]), Dual(f.q0[1]), Dual(f.q0[2]), Dual(f.q0[3])}, q0c[4], dq[4]; qconj(q0, q0c); qmul(q0c, q, dq);
+    for (int c = 0; c < 3; ++c) res[3 + c] = Dual(f.sw[3 + c]) * (Dual(2.0) * dq[1 + c]);
+    for (int c = 0; c < 9; ++c) res[6 + c] = Dual(f.sw[6 + c]) * (Dual(xa[7 + c], 7 + c) - Dual(f.sb0[c]));
+    construct_A(N, A, b, 15, res, 0, -1);
+  }
+  for (const Between& f : P.betweens) {
+    if (!(f.i == 0 && f.j == 1)) continue;
+    const double* xi = x; const double* xj = x + P.na;
+    Dual ti[3] = {Dual(xi[0], 0), Dual(xi[1], 1), Dual(xi[2], 2)}, qi[4] = {Dual(xi[3], 3), Dual(xi[4], 4), Dual(xi[5], 5), Dual(xi[6], 6)};
+    Dual tj[3] = {Dual(xj[0], 16), Dual(xj[1], 17), Dual(xj[2], 18)}, qj[4] = {Dual(xj[3], 19), Dual(xj[4], 20), Dual(xj[5], 21), Dual(xj[6], 22)};
+    Dual vi[3], vj[3], bi[6], bj[6];
+    for (int c = 0; c < 3; ++c) { vi[c] = Dual(xi[7 + c], 7 + c); vj[c] = Dual(xj[7 + c], 23 + c); }
+    for (int c = 0; c < 6; ++c) { bi[c] = Dual(xi[10 + c], 10 + c); bj[c] = Dual(xj[10 + c], 26 + c); }
+    Dual qic[4]; qconj(qi, qic);
+    Dual d[3] = {tj[0] - ti[0] - vi[0] * Dual(f.dt), tj[1] - ti[1] - vi[1] * Dual(f.dt), tj[2] - ti[2] - vi[2] * Dual(f.dt)}, rp[3]; qrot(qic, d, rp);
+    Dual res[15];
+    for (int c = 0; c < 3; ++c) res[c] = Dual(f.sw[c]) * (rp[c] - Dual(f.dp[c]));
+    Dual dqc[4] = {Dual(f.dq[0]), Dual(-f.dq[1]), Dual(-f.dq[2]), Dual(-f.dq[3])}, qij[4], e[4]; qmul(qic, qj, qij); qmul(dqc, qij, e);
+    for (int c = 0; c < 3; ++c) res[3 + c] = Dual(f.sw[3 + c]) * (Dual(2.0) * e[1 + c]);
+    Dual dvv[3] = {vj[0] - vi[0], vj[1] - vi[1], vj[2] - vi[2]}, rv[3]; qrot(qic, dvv, rv);
+    for (int c = 0; c < 3; ++c) res[6 + c] = Dual(f.sw[6 + c]) * (rv[c] - Dual(f.dv[c]));
+    for (int c = 0; c < 6; ++c) res[9 + c] = Dual(f.sw[9 + c]) * (bj[c] - bi[c]);
+    construct_A(N, A, b, 15, res, 0, 1);
+  }
+  if (P.marg.n > 0) {
+    if (P.marg.W != W) return -2;
+    MargEval E; marg_prior_eval(P, x, E);
+    const int np = P.marg.n;
+    for (int r = 0; r < np; ++r) {
+      int col[160]; double val[160]; int nz = 0;
+      for (int k = 0; k <= W - 2; ++k) {
+        const double* dv = &E.Jamb[k][(size_t)r * 16]; const int base = marg_off(k);
+        for (int c = 0; c < 3; ++c) { col[nz] = base + c; val[nz++] = dv[c]; }
+        for (int c = 0; c < 3; ++c) { col[nz] = base + 3 + c; val[nz++] = dv[4 + c]; }
+        if (k == 0) for (int c = 0; c < 9; ++c) { col[nz] = base + 6 + c; val[nz++] = dv[7 + c]; }
+      }
+      for (int i = 0; i < nz; ++i) { if (val[i] == 0.0) continue; b[col[i]] += val[i] * E.res[r]; for (int j = 0; j < nz; ++j) A[(size_t)col[i] * N + col[j]] += val[i] * val[j]; }
+    }
+  }
+  if (A_out) std::memcpy(A_out, A.data(), sizeof(double) * A.size());
+  if (b_out) std::memcpy(b_out, b.data(), sizeof(double) * b.size());
+  // Marginalize (:176-201)
+  std::vector<double> Amm((size_t)m * m), w, V;
+  for (int i = 0; i < m; ++i) for (int j = 0; j < m; ++j) Amm[(size_t)i * m + j] = 0.5 * (A[(size_t)i * N + j] + A[(size_t)j * N + i]);
+  jacobi_eigh(Amm, m, w, V);
+  std::vector<double> Ainv((size_t)m * m, 0.0);
+  for (int k = 0; k < m; ++k) { if (!(w[k] > eps)) continue; for (int i = 0; i < m; ++i) for (int j = 0; j < m; ++j) Ainv[(size_t)i * m + j] += V[(size_t)i * m + k] * V[(size_t)j * m + k] / w[k]; }
+  std::vector<double> T((size_t)n * m, 0.0), Ar((size_t)n * n), br(n);
+  for (int i = 0; i < n; ++i) for (int k = 0; k < m; ++k) for (int j = 0; j < m; ++j) T[(size_t)i * m + j] += A[(size_t)(m + i) * N + k] * Ainv[(size_t)k * m + j];
+  for (int i = 0; i < n; ++i) {
+    double sacc = b[m + i]; for (int k = 0; k < m; ++k) sacc -= T[(size_t)i * m + k] * b[k]; br[i] = sacc;
+    for (int j = 0; j < n; ++j) { double v = A[(size_t)(m + i) * N + m + j]; for (int k = 0; k < m; ++k) v -= T[(size_t)i * m + k] * A[(size_t)k * N + m + j]; Ar[(size_t)i * n + j] = v; }
+  }
+  for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) Ar[(size_t)j * n + i] = Ar[(size_t)i * n + j];     // SelfAdjointEigenSolver reads the lower triangle
+  std::vector<double> w2, V2; jacobi_eigh(Ar, n, w2, V2);
+  for (int k = 0; k < n; ++k) {
+    const double S = w2[k] > eps ? w2[k] : 0.0, Si = w2[k] > eps ? 1.0 / w2[k] : 0.0; double vb = 0;
+    for (int j = 0; j < n; ++j) { lin_jac[(size_t)k * n + j] = std::sqrt(S) * V2[(size_t)j * n + k]; vb += V2[(size_t)j * n + k] * br[j]; }
+    lin_res[k] = std::sqrt(Si) * vb;
+  }
+  // keep_block_data in the next window's numbering (addr_shift, Estimator.cpp:2583-2597)
+  for (int k = 1; k < W; ++k) for (int i = 0; i < 7; ++i) x0_pose[(size_t)7 * (k - 1) + i] = x[(size_t)P.na * k + i];
+  for (int c = 0; c < 9; ++c) x0_sb[c] = x[(size_t)P.na + 7 + c];
+  return 0;
 }
 
 int go_problem_solve(void* h, const void* options, int mode, int nthreads, void* summary_out, void* iter_log, int iter_cap,

@@ -266,6 +266,22 @@ class WindowProblem:
     def add_range(self, kf, lever, sat, rho, w):
         lib().go_problem_add_range(self.h, C.c_int(kf), _p(_f64(lever)), _p(_f64(sat)), C.c_double(rho), C.c_double(w))
 
+    def set_marg_prior(self, prior):
+        """prior: dict(W, lin_jac, lin_res, x0_pose, x0_sb) in the numbering of THIS window (None removes it)."""
+        if prior is None:
+            lib().go_problem_set_marg_prior(self.h, C.c_int(0), None, None, None, None)
+            return
+        a = [_f64(prior[k]) for k in ("lin_jac", "lin_res", "x0_pose", "x0_sb")]
+        lib().go_problem_set_marg_prior(self.h, C.c_int(int(prior["W"])), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]))
+
+    def marginalize(self, eps=1e-8, mode=0):
+        """MarginalizationInfo::PreMarginalize + Marginalize at the problem's current state (GLIO/src/MarginalizationFactor.cpp:107-202)."""
+        W = self.W; N = 6 * W + 18; n = N - 15
+        out = dict(W=W, lin_jac=np.zeros((n, n)), lin_res=np.zeros(n), x0_pose=np.zeros((W - 1, 7)), x0_sb=np.zeros(9), A=np.zeros((N, N)), b=np.zeros(N))
+        rc = lib().go_problem_marginalize(self.h, C.c_double(eps), C.c_int(mode), _p(out["lin_jac"]), _p(out["lin_res"]), _p(out["x0_pose"]), _p(out["x0_sb"]), _p(out["A"]), _p(out["b"]))
+        assert rc == 0, rc
+        return out
+
     def reset_state(self, poses, speed_bias=None):
         pb = _f64(poses).reshape(-1, 7); sb = None if speed_bias is None else _f64(speed_bias).reshape(-1, 9)
         lib().go_problem_set_state(self.h, _p(pb), _p(sb))

@@ -98,3 +98,24 @@ def test_null_context_is_an_argument_error_not_a_crash():
     for name, args in calls:
         f = getattr(lib, name); f.restype = ctypes.c_int
         assert f(*args) == -3, name          # GLIO_ERR_ARG
+
+
+def test_band_callback_rejects_a_too_narrow_band():
+    """a host Hessian entry outside the declared half bandwidth must be an error, not silently dropped (a wrong
+    band would give a wrong J^T J with no sign of it)."""
+    import ctypes as C
+    import numpy as np
+    from glio_b200 import api, synth
+    rng = np.random.default_rng(0)
+    T = synth.trajectory(3, rng)
+    hf = api.HostFactorSet()
+    sw = np.concatenate([np.full(3, 20.0), np.full(3, 50.0), np.full(9, 5.0)])
+    hf.add_between(0, 1, np.zeros(3), np.array([1.0, 0, 0, 0]), np.zeros(3), 0.1, sw)
+    L = api.lib()
+    n = 45
+    sb = np.zeros((3, 9)); g = np.zeros(n); cost = np.zeros(1)
+    for hb, want_ok in ((29, True), (10, False)):
+        Hb = np.zeros(n * (hb + 1))
+        rc = L.glio_hf_evaluate_band(hf._h, C.c_int(3), T.ctypes.data_as(C.c_void_p), sb.ctypes.data_as(C.c_void_p), C.c_int(1),
+                                     Hb.ctypes.data_as(C.c_void_p), C.c_int(hb), g.ctypes.data_as(C.c_void_p), cost.ctypes.data_as(C.c_void_p))
+        assert (rc == 0) == want_ok, (hb, rc)

@@ -57,3 +57,26 @@ def test_window_associate_equals_single_calls(ctx, oracle):
         t2, q2 = ctx.lidar_pose(P["poses_init"][k])
         o = _check_slot(ctx, oracle, P, k, t2, q2, tree)
         assert nm[k] == o["nvalid"]
+
+
+def test_window_slide_equals_fresh_window(ctx, oracle):
+    """slideWindow on the device: after glio_window_slide + one new scan in the last slot, the association of the shifted
+    window equals the association of the same keyframes handed over from scratch (scans and matches moved with their slots)."""
+    W = 4
+    P = synth.window_problem(W=W + 1, Q=2500, M=40000, seed=23)
+    ctx.set_map(P["map_xyz"])
+    ctx.window_set_scans(P["scans"][:W])
+    ctx.window_associate(P["poses_init"][:W])
+    ctx.window_slide(W)
+    ctx.window_set_scan(W - 1, P["scans"][W])
+    nm = ctx.window_associate(P["poses_init"][1:W + 1])
+    snap = [(ctx.get_assoc_debug(k, 2500), ctx.get_matches(k, 2500)) for k in range(W)]
+    ctx.window_set_scans(P["scans"][1:W + 1])
+    nm2 = ctx.window_associate(P["poses_init"][1:W + 1])
+    assert np.array_equal(nm, nm2)
+    for k in range(W):
+        d, m = ctx.get_assoc_debug(k, 2500), ctx.get_matches(k, 2500)
+        for key in ("status", "idx5", "sqd5", "plane"):
+            assert np.array_equal(d[key], snap[k][0][key])
+        for key in ("cp", "nsd", "weight", "src"):
+            assert np.array_equal(m[key], snap[k][1][key])
