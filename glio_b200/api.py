@@ -134,7 +134,7 @@ class Context:
         self._lib.glio_lidar_pose(C.byref(self.params), _ptr(pb), _ptr(t2), _ptr(q2))
         return t2, q2
 
-    KERNELS = ["k_knn_tile", "k_knn_tile2", "k_defer_scatter", "k_knn_team", "k_make_pairs", "k_knn_search", "k_knn_deferred", "k_knn_thread", "k_knn_box", "k_plane_fit", "k_plane_fit_pair", "k_eval_unary", "k_eval_unary_cost", "k_transform_hist", "k_order_scatter",
+    KERNELS = ["k_feat_curvature", "k_feat_select", "k_feat_voxel", "k_feat_offsets", "k_feat_gather", "k_knn_tile", "k_knn_tile2", "k_defer_scatter", "k_knn_team", "k_make_pairs", "k_knn_search", "k_knn_deferred", "k_knn_thread", "k_knn_box", "k_plane_fit", "k_plane_fit_pair", "k_eval_unary", "k_eval_unary_cost", "k_transform_hist", "k_order_scatter",
                "k_compact", "k_flags", "k_cell_hist", "k_cell_scatter", "k_load_bounds", "k_scan_block", "k_scan_add",
                "k_eval_binary", "k_eval_binary_cost", "k_bin_assemble",
                "k_lm_transform", "k_vox_hist", "k_vox_scatter", "k_vox_sort", "k_vox_flags", "k_vox_centroid", "k_init_bounds"]
@@ -378,6 +378,26 @@ class HostFactorSet:
                 self._lib.glio_hf_destroy(self._h); self._h = None
         except Exception:
             pass
+
+
+def _extract_features(self, cloud_xyzi, scan_start, scan_end, ds_rate=1, edge_thres=1.0, surf_thres=0.1, ds_v=0.4, intensity_offset=None):
+    """Preprocessing::cloudHandler's feature extraction (GLIO/src/Preprocessing.cpp:529-655) on the device."""
+    keep, p, n, stride, mem = _points_arg(cloud_xyzi)
+    ioff = intensity_offset if intensity_offset is not None else (4 if stride == 8 else 3)
+    ss = np.ascontiguousarray(scan_start, np.int32); se = np.ascontiguousarray(scan_end, np.int32); S = len(ss)
+    out = dict(curvature=np.empty(n, np.float32), label=np.empty(n, np.int8), sharp=np.empty(12 * S, np.int32), less_sharp=np.empty(60 * S, np.int32),
+               flat=np.empty(24 * S, np.int32), less_flat=np.empty(n, np.int32), less_flat_ds=np.empty((n, 4), np.float32))
+    cnt = [C.c_int64(0) for _ in range(5)]
+    self._chk(self._lib.glio_extract_features(self._h, p, C.c_int64(n), C.c_int(stride), C.c_int(ioff), C.c_int(mem), C.c_int(S), _ptr(ss), _ptr(se), C.c_int(ds_rate),
+                                              C.c_double(edge_thres), C.c_double(surf_thres), C.c_float(ds_v), _ptr(out["curvature"]), _ptr(out["label"]),
+                                              _ptr(out["sharp"]), C.byref(cnt[0]), _ptr(out["less_sharp"]), C.byref(cnt[1]), _ptr(out["flat"]), C.byref(cnt[2]),
+                                              _ptr(out["less_flat"]), C.byref(cnt[3]), _ptr(out["less_flat_ds"]), C.byref(cnt[4])))
+    for k, c in zip(("sharp", "less_sharp", "flat", "less_flat", "less_flat_ds"), cnt):
+        out[k] = out[k][:c.value]
+    return out
+
+
+Context.extract_features = _extract_features
 
 
 HOST_MARG_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double))

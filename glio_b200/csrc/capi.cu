@@ -101,6 +101,8 @@ struct glio_ctx {
   PinnedBuf<int> h_counts;
   DevBuf<int> d_bad;
   DevBuf<int32_t> d_keep;
+  // front-end feature extraction work space
+  DevBuf<float> f_cloud, f_curv; DevBuf<int8_t> f_label, f_picked; DevBuf<int32_t> f_scan, f_ring, f_lf, f_counts, f_out; DevBuf<float4> f_ds, f_outds;
   // K2e scratch (kept in the context: no cudaMalloc / cudaFree per call, nothing to leak when a call throws)
   DevBuf<EdgeItem> e_items; DevBuf<int> e_start; DevBuf<double> e_part, e_out, e_poses;
 
@@ -423,6 +425,7 @@ void glio_destroy(glio_ctx* c) {
   c->h_counts.release(); c->d_bad.release(); c->d_keep.release(); c->d_items.release(); c->d_kf_item_start.release();
   c->d_partials.release(); c->d_out.release(); c->d_poses.release(); c->d_r.release(); c->d_J.release(); c->h_out.release();
   c->h_poses.release(); c->h_flag.release(); c->d_ticket.release(); c->w_knn_idx.release(); c->w_knn_sqd.release(); c->d_stats.release(); c->w_deferred.release();
+  c->f_cloud.release(); c->f_curv.release(); c->f_label.release(); c->f_picked.release(); c->f_scan.release(); c->f_ring.release(); c->f_lf.release(); c->f_counts.release(); c->f_out.release(); c->f_ds.release(); c->f_outds.release();
   c->e_items.release(); c->e_start.release(); c->e_part.release(); c->e_out.release(); c->e_poses.release();
   for (auto& r : c->lc.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto& e : c->lc.pool) cudaEventDestroy(e);
@@ -811,21 +814,73 @@ int glio_window_marginalize(glio_ctx* c, int W, const double* poses, const doubl
     const int N = 6 * W + 18, m = 15, n = N - m;
     // LiDAR factors of every keyframe of the window with the ambient x,y,z quaternion columns (Estimator.cpp:2538-2576):
     // device pass -> W x (21 upper-triangular H, 6 g, cost) in pinned host memory
-    eval_unary_blocks(c, W, poses, 1, true);
+    const unsigned int epoch = eval_unary_launch(c, W, poses, 1, true);
     std::vector<double> A((size_t)N * N, 0.0), b(N, 0.0);
+    // the host factors are evaluated while the kernel runs
+    if (host_marg) GLIO_REQUIRE(host_marg(user, W, poses, speed_bias, A.data(), b.data()) == 0, GLIO_ERR_STATE, "host_marg callback failed");
+    eval_unary_wait(c, epoch);
     static const int ut[6][6] = {{0, 1, 2, 3, 4, 5}, {1, 6, 7, 8, 9, 10}, {2, 7, 11, 12, 13, 14}, {3, 8, 12, 15, 16, 17}, {4, 9, 13, 16, 18, 19}, {5, 10, 14, 17, 19, 20}};
     for (int k = 0; k < W; ++k) {
       const double* o = c->h_out.p + (size_t)k * GLIO_NACC;
       const int base = marg_index_t(k);                       // t at base, q at base + 3 in every keyframe of this ordering
       for (int p = 0; p < 6; ++p) { b[base + p] += o[21 + p]; for (int q = 0; q < 6; ++q) A[(size_t)(base + p) * N + base + q] += o[ut[p][q]]; }
     }
-    if (host_marg) GLIO_REQUIRE(host_marg(user, W, poses, speed_bias, A.data(), b.data()) == 0, GLIO_ERR_STATE, "host_marg callback failed");
-    std::unique_ptr<glio_marg_prior> P(new glio_marg_prior());
     std::vector<double> LJ((size_t)n * n), lr(n);
     GLIO_REQUIRE(marginalize_dense(A.data(), b.data(), N, m, eps, LJ.data(), lr.data()) == GLIO_OK, GLIO_ERR_STATE, "marginalize_dense failed");
     glio_marg_prior* made = glio_marg_prior_create(W, LJ.data(), lr.data(), poses + 7, speed_bias + 9);
     GLIO_REQUIRE(made != nullptr, GLIO_ERR_STATE, "glio_marg_prior_create failed");
     *prior_out = made;
+  });
+}
+
+// ---- front-end feature extraction: Preprocessing::cloudHandler, GLIO/src/Preprocessing.cpp:529-655
+int glio_extract_features(glio_ctx* c, const float* cloud_xyzi, int64_t n, int stride, int intensity_offset, int mem, int n_scans, const int32_t* scan_start,
+                          const int32_t* scan_end, int ds_rate, double edge_thres, double surf_thres, float ds_v, float* curvature, int8_t* label,
+                          int32_t* sharp, int64_t* n_sharp, int32_t* less_sharp, int64_t* n_less_sharp, int32_t* flat, int64_t* n_flat,
+                          int32_t* less_flat, int64_t* n_less_flat, float* less_flat_ds, int64_t* n_less_flat_ds) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(cloud_xyzi && n > 10 && n < ((int64_t)1 << 30), GLIO_ERR_ARG, "glio_extract_features: bad cloud");
+    GLIO_REQUIRE(stride >= 4 && stride <= 64 && intensity_offset >= 3 && intensity_offset < stride, GLIO_ERR_ARG, "glio_extract_features: stride_floats must be >= 4 and 3 <= intensity_offset < stride");
+    GLIO_REQUIRE(n_scans > 0 && n_scans <= 1024 && scan_start && scan_end && ds_rate >= 1 && ds_v > 0.f, GLIO_ERR_ARG, "glio_extract_features: bad ring table");
+    for (int r = 0; r < n_scans; ++r) GLIO_REQUIRE(scan_start[r] >= 5 && scan_end[r] < n - 5 && scan_end[r] - scan_start[r] < n, GLIO_ERR_ARG, "glio_extract_features: ring range outside [5, n-6]");
+    FeatArgs a{};
+    const float* d_cloud = cloud_xyzi;
+    if (mem != GLIO_DEVICE) { c->f_cloud.reserve((size_t)n * stride); GLIO_CUDA_TRY(cudaMemcpyAsync(c->f_cloud.p, cloud_xyzi, (size_t)n * stride * sizeof(float), cudaMemcpyHostToDevice, c->st)); d_cloud = c->f_cloud.p; }
+    c->f_curv.reserve(n); c->f_label.reserve(n); c->f_picked.reserve(n); c->f_scan.reserve((size_t)2 * n_scans);
+    c->f_ring.reserve((size_t)n_scans * (FEAT_MAX_SHARP + FEAT_MAX_LESS_SHARP + FEAT_MAX_FLAT)); c->f_lf.reserve(n); c->f_ds.reserve(n);
+    c->f_counts.reserve((size_t)5 * n_scans + (size_t)5 * (n_scans + 1) + 4);
+    c->f_out.reserve((size_t)n_scans * (FEAT_MAX_SHARP + FEAT_MAX_LESS_SHARP + FEAT_MAX_FLAT) + n); c->f_outds.reserve(n);
+    GLIO_CUDA_TRY(cudaMemcpyAsync(c->f_scan.p, scan_start, n_scans * sizeof(int32_t), cudaMemcpyHostToDevice, c->st));
+    GLIO_CUDA_TRY(cudaMemcpyAsync(c->f_scan.p + n_scans, scan_end, n_scans * sizeof(int32_t), cudaMemcpyHostToDevice, c->st));
+    a.cloud = d_cloud; a.stride = stride; a.ioff = intensity_offset; a.n = n; a.n_scans = n_scans; a.scan_start = c->f_scan.p; a.scan_end = c->f_scan.p + n_scans; a.ds_rate = ds_rate;
+    a.edge_thres = edge_thres; a.surf_thres = surf_thres; a.ds_v = ds_v;
+    a.curv = c->f_curv.p; a.label = c->f_label.p; a.picked = c->f_picked.p;
+    a.ring_sharp = c->f_ring.p; a.ring_less_sharp = a.ring_sharp + (size_t)n_scans * FEAT_MAX_SHARP; a.ring_flat = a.ring_less_sharp + (size_t)n_scans * FEAT_MAX_LESS_SHARP;
+    a.ring_less_flat = c->f_lf.p; a.ring_ds = c->f_ds.p;
+    a.counts = c->f_counts.p; a.offsets = c->f_counts.p + 5 * n_scans; a.err = c->f_counts.p + 5 * n_scans + 5 * (n_scans + 1);
+    a.out_sharp = c->f_out.p; a.out_less_sharp = a.out_sharp + (size_t)n_scans * FEAT_MAX_SHARP; a.out_flat = a.out_less_sharp + (size_t)n_scans * FEAT_MAX_LESS_SHARP;
+    a.out_less_flat = a.out_flat + (size_t)n_scans * FEAT_MAX_FLAT; a.out_ds = c->f_outds.p;
+    features_run(a, c->st, c->lc);
+    std::vector<int32_t> tot((size_t)5 * (n_scans + 1) + 1);
+    GLIO_CUDA_TRY(cudaMemcpyAsync(tot.data(), a.offsets, tot.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+    const int32_t err = tot[(size_t)5 * (n_scans + 1)];
+    GLIO_REQUIRE(err == 0, GLIO_ERR_ARG, err == 1 ? "glio_extract_features: a ring sector has more than 4096 points" : "glio_extract_features: a ring has more than 8192 less-flat points");
+    const int64_t cnt[5] = {tot[0 * (n_scans + 1) + n_scans], tot[1 * (n_scans + 1) + n_scans], tot[2 * (n_scans + 1) + n_scans], tot[3 * (n_scans + 1) + n_scans], tot[4 * (n_scans + 1) + n_scans]};
+    if (n_sharp) *n_sharp = cnt[0];
+    if (n_less_sharp) *n_less_sharp = cnt[1];
+    if (n_flat) *n_flat = cnt[2];
+    if (n_less_flat) *n_less_flat = cnt[3];
+    if (n_less_flat_ds) *n_less_flat_ds = cnt[4];
+    if (curvature) GLIO_CUDA_TRY(cudaMemcpyAsync(curvature, a.curv, n * sizeof(float), cudaMemcpyDeviceToHost, c->st));
+    if (label) GLIO_CUDA_TRY(cudaMemcpyAsync(label, a.label, n, cudaMemcpyDeviceToHost, c->st));
+    if (sharp && cnt[0]) GLIO_CUDA_TRY(cudaMemcpyAsync(sharp, a.out_sharp, cnt[0] * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+    if (less_sharp && cnt[1]) GLIO_CUDA_TRY(cudaMemcpyAsync(less_sharp, a.out_less_sharp, cnt[1] * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+    if (flat && cnt[2]) GLIO_CUDA_TRY(cudaMemcpyAsync(flat, a.out_flat, cnt[2] * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+    if (less_flat && cnt[3]) GLIO_CUDA_TRY(cudaMemcpyAsync(less_flat, a.out_less_flat, cnt[3] * sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+    if (less_flat_ds && cnt[4]) GLIO_CUDA_TRY(cudaMemcpyAsync(less_flat_ds, a.out_ds, cnt[4] * sizeof(float4), cudaMemcpyDeviceToHost, c->st));
+    GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
   });
 }
 

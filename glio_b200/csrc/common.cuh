@@ -251,4 +251,22 @@ void eval_binary_run(const BinItem* d_items, int nitems, const int* d_pair_item_
                      const int* d_kf_inc_start, const BinIncidence* d_inc, double* d_diag /*K*28*/, double* d_off /*n_pairs*36*/,
                      double* d_cost, cudaStream_t st, LaunchCounter& lc);
 
+// ---- front-end feature extraction (features.cu; Preprocessing.cpp:529-655)
+constexpr int FEAT_MAX_SHARP = 12, FEAT_MAX_LESS_SHARP = 60, FEAT_MAX_FLAT = 24;   // per ring: 6 sectors x (2, 10, 4)
+struct FeatArgs {
+  const float* cloud; int stride; int ioff; int64_t n;     // ioff: float offset of the intensity (3 packed, 4 in pcl::PointXYZI)
+  int n_scans; const int32_t* scan_start; const int32_t* scan_end; int ds_rate;
+  double edge_thres, surf_thres; float ds_v;
+  float* curv; int8_t* label; int8_t* picked;
+  int32_t* ring_sharp; int32_t* ring_less_sharp; int32_t* ring_flat;   // [n_scans][MAX] slots
+  int32_t* ring_less_flat;                                             // [n] ring r's list starts at scan_start[r]
+  float4* ring_ds;                                                     // [n] ring r's down-sampled points start at scan_start[r]
+  int32_t* counts;                                                     // [5][n_scans]: sharp, less_sharp, flat, less_flat, ds
+  int32_t* offsets;                                                    // [5][n_scans + 1]
+  int32_t* err;                                                        // != 0: a sector / ring exceeded the shared-memory capacity
+  int32_t* out_sharp; int32_t* out_less_sharp; int32_t* out_flat; int32_t* out_less_flat; float4* out_ds;
+};
+
+void features_run(FeatArgs& a, cudaStream_t st, LaunchCounter& lc);
+
 }  // namespace glio

@@ -178,14 +178,23 @@ int marginalize_dense(const double* A, const double* b, int n_total, int m, doub
   }
   std::vector<double> Ar((size_t)n * n), br(n);
   for (int i = 0; i < n; ++i) {
+    // rows that are not coupled to the dropped states (all of T's row is zero) are copied as they are
+    bool coupled = false;
+    for (int k = 0; k < m; ++k) if (T[(size_t)i * m + k] != 0.0) { coupled = true; break; }
+    const double* arow = A + (size_t)(m + i) * N + m;
+    double* orow = &Ar[(size_t)i * n];
+    std::memcpy(orow, arow, sizeof(double) * (size_t)n);
     double s = b[m + i];
-    for (int k = 0; k < m; ++k) s -= T[(size_t)i * m + k] * b[k];
-    br[i] = s;
-    for (int j = 0; j < n; ++j) {
-      double v = A[(size_t)(m + i) * N + m + j];
-      for (int k = 0; k < m; ++k) { const double t = T[(size_t)i * m + k]; if (t != 0.0) v -= t * A[(size_t)k * N + m + j]; }
-      Ar[(size_t)i * n + j] = v;
+    if (coupled) {
+      for (int k = 0; k < m; ++k) {
+        const double t = T[(size_t)i * m + k];
+        if (t == 0.0) continue;
+        s -= t * b[k];
+        const double* amr = A + (size_t)k * N + m;
+        for (int j = 0; j < n; ++j) orow[j] -= t * amr[j];
+      }
     }
+    br[i] = s;
   }
   // symmetrise before the second decomposition (SelfAdjointEigenSolver reads the lower triangle only)
   for (int i = 0; i < n; ++i) for (int j = 0; j < i; ++j) Ar[(size_t)j * n + i] = Ar[(size_t)i * n + j];

@@ -173,3 +173,37 @@ def batch_problem(K=200, Q=100_000, seed=SEED0 + 3, search_range=6, rng_range=50
     want = set(range(K)) if frames is None else set(int(f) for f in frames)
     scans = [scan_in_body_frame(scene, truth[k], Q, np.random.default_rng([seed, k]), rng_range) if k in want else None for k in range(K)]
     return dict(scans=scans, poses_true=truth, poses_init=init, K=K, Q=Q, search_range=search_range, seed=seed)
+
+
+def ring_scan(n_rings=32, n_az=1500, seed=SEED0 + 11, fov=(-25.0, 15.0), noise=0.01, drop=0.02):
+    """A spinning-LiDAR sweep of the street-canyon scene, ring by ring, for the front end's feature extraction:
+    rays are cast from the sensor against the scene's rectangles (nearest hit), range noise N(0, noise), a fraction `drop` of the
+    returns missing.  Returns (cloud (n,4) float32: x,y,z,intensity = ring + 0.1 relTime; scan_start, scan_end int32 arrays) laid
+    out as Preprocessing::cloudHandler lays out `laserCloud` (GLIO/src/Preprocessing.cpp:529-534): rings concatenated,
+    scanStartInd = first index + 5, scanEndInd = last index - 5."""
+    rng = np.random.default_rng(seed)
+    sc = Scene(-60.0, 60.0, rng)
+    origin = np.array([0.3, -0.4, 0.2])
+    elev = np.deg2rad(np.linspace(fov[0], fov[1], n_rings))
+    clouds, start, end = [], [], []
+    total = 0
+    for r in range(n_rings):
+        az = np.linspace(0.0, 2 * np.pi, n_az, endpoint=False) + rng.uniform(0, 1e-3)
+        d = np.stack([np.cos(elev[r]) * np.cos(az), np.cos(elev[r]) * np.sin(az), np.full(n_az, np.sin(elev[r]))], 1)
+        best = np.full(n_az, np.inf)
+        for o, u, v, nrm in zip(sc.o, sc.u, sc.v, sc.n):
+            den = d @ nrm
+            with np.errstate(divide="ignore", invalid="ignore"):
+                t = ((o - origin) @ nrm) / den
+            hit = origin + t[:, None] * d - o
+            a = (hit @ u) / (u @ u); b = (hit @ v) / (v @ v)
+            ok = (np.abs(den) > 1e-9) & (t > 0.5) & (a >= 0) & (a <= 1) & (b >= 0) & (b <= 1)
+            best = np.where(ok & (t < best), t, best)
+        keep = np.isfinite(best) & (best < 80.0) & (rng.random(n_az) > drop)
+        rg = best[keep] + rng.normal(0.0, noise, int(keep.sum()))
+        pts = origin + rg[:, None] * d[keep]
+        rel = az[keep] / (2 * np.pi)
+        cl = np.concatenate([pts, (r + 0.1 * rel)[:, None]], 1).astype(np.float32)
+        clouds.append(cl)
+        start.append(total + 5); total += len(cl); end.append(total - 6)
+    return np.concatenate(clouds), np.asarray(start, np.int32), np.asarray(end, np.int32)

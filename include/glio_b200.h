@@ -252,6 +252,19 @@ void glio_hf_add_between(glio_host_factor_set* s, int i, int j, const double dp[
 void glio_hf_add_range(glio_host_factor_set* s, int kf, const double lever[3], const double sat[3], double rho, double w);
 int glio_hf_evaluate(void* user, int W, const double* poses, const double* speed_bias, int want_jac, double* H, double* g, double* cost);
 
+/* ---- front-end feature extraction: Preprocessing::cloudHandler, GLIO/src/Preprocessing.cpp:529-655.
+ * cloud_xyzi = `laserCloud` of the reference: the scan lines concatenated ring after ring, x,y,z,intensity at stride_floats
+ * (>= 4) with the intensity at float intensity_offset (packed x,y,z,i: stride 4, offset 3; pcl::PointXYZI: stride 8, offset 4),
+ * scan_start / scan_end = scanStartInd / scanEndInd per ring (:529-534; every range inside
+ * [5, n-6]).  Outputs, any may be NULL: cloudCurvature[n], cloudLabel[n] (2 sharp, 1 less sharp, -1 flat, 0 other), and the
+ * four feature sets in the reference's push_back order as indices into the cloud (cornerPointsSharp, cornerPointsLessSharp,
+ * surfPointsFlat, the less-flat points BEFORE the voxel filter) plus surfPointsLessFlat itself (x,y,z,intensity after the
+ * per-ring pcl::VoxelGrid of leaf ds_v).  Equal curvatures are ordered by index (std::sort leaves it open). */
+int glio_extract_features(glio_ctx* ctx, const float* cloud_xyzi, int64_t n, int stride_floats, int intensity_offset, int mem, int n_scans, const int32_t* scan_start,
+                          const int32_t* scan_end, int ds_rate, double edge_thres, double surf_thres, float ds_v, float* curvature, int8_t* label,
+                          int32_t* sharp, int64_t* n_sharp, int32_t* less_sharp, int64_t* n_less_sharp, int32_t* flat, int64_t* n_flat,
+                          int32_t* less_flat, int64_t* n_less_flat, float* less_flat_ds, int64_t* n_less_flat_ds);
+
 /* ---- K3: marginalisation of the oldest keyframe (MarginalizationInfo, GLIO/src/MarginalizationFactor.cpp:82-202; call site
  * Estimator.cpp:2462-2608).  The reference re-evaluates EVERY LiDAR factor of the window (:2538-2576, one virtual Evaluate per
  * residual) plus the IMU factor KF0->KF1 and the previous prior, accumulates the dense A = J^T J, b = J^T r with the ambient

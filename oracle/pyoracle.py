@@ -91,6 +91,23 @@ def knn5_brute(map_xyz, qry_xyz):
     return idx, sqd, tie
 
 
+def extract_features(cloud_xyzi, scan_start, scan_end, ds_rate=1, edge_thres=1.0, surf_thres=0.1, ds_v=0.4, stable=True):
+    """Preprocessing::cloudHandler's feature extraction (GLIO/src/Preprocessing.cpp:529-655); see glio_oracle_features.cpp."""
+    cl = _f32(cloud_xyzi).reshape(-1, 4); n = len(cl)
+    ss = np.ascontiguousarray(scan_start, np.int32); se = np.ascontiguousarray(scan_end, np.int32); S = len(ss)
+    out = dict(curvature=np.empty(n, np.float32), label=np.empty(n, np.int8), sharp=np.empty(12 * S, np.int32), less_sharp=np.empty(60 * S, np.int32),
+               flat=np.empty(24 * S, np.int32), less_flat=np.empty(n, np.int32), less_flat_ds=np.empty((n, 4), np.float32), ring_ds_count=np.empty(S, np.int32))
+    cnt = [C.c_int64(0) for _ in range(5)]
+    rc = lib().go_extract_features(_p(cl), C.c_int64(n), C.c_int(S), _p(ss), _p(se), C.c_int(ds_rate), C.c_double(edge_thres), C.c_double(surf_thres),
+                                   C.c_float(ds_v), C.c_int(1 if stable else 0), _p(out["curvature"]), _p(out["label"]), _p(out["sharp"]), C.byref(cnt[0]),
+                                   _p(out["less_sharp"]), C.byref(cnt[1]), _p(out["flat"]), C.byref(cnt[2]), _p(out["less_flat"]), C.byref(cnt[3]),
+                                   _p(out["less_flat_ds"]), C.byref(cnt[4]), _p(out["ring_ds_count"]))
+    assert rc == 0
+    for k, c in zip(("sharp", "less_sharp", "flat", "less_flat", "less_flat_ds"), cnt):
+        out[k] = out[k][:c.value]
+    return out
+
+
 class KdTree:
     def __init__(self, xyz):
         self.xyz = _f32(xyz).reshape(-1, 3)

@@ -36,11 +36,14 @@ def main():
         try:
             n = int(count)
             h = np.empty(n, np.float64)
-            cudart.cudaStreamSynchronize(C.c_void_p(stream))
-            assert cudart.cudaMemcpy(h.ctypes.data_as(C.c_void_p), C.c_void_p(d_buf), C.c_size_t(8 * n), C.c_int(2)) == 0
+            # everything on the library's own (non-blocking) stream: a copy on the NULL stream would not be ordered with it
+            s = C.c_void_p(stream)
+            assert cudart.cudaMemcpyAsync(h.ctypes.data_as(C.c_void_p), C.c_void_p(d_buf), C.c_size_t(8 * n), C.c_int(2), s) == 0
+            assert cudart.cudaStreamSynchronize(s) == 0
             t = torch.from_numpy(h)
             dist.all_reduce(t)
-            assert cudart.cudaMemcpy(C.c_void_p(d_buf), h.ctypes.data_as(C.c_void_p), C.c_size_t(8 * n), C.c_int(1)) == 0
+            assert cudart.cudaMemcpyAsync(C.c_void_p(d_buf), h.ctypes.data_as(C.c_void_p), C.c_size_t(8 * n), C.c_int(1), s) == 0
+            assert cudart.cudaStreamSynchronize(s) == 0
             calls[0] += 1
             return 0
         except Exception:
