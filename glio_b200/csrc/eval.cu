@@ -189,8 +189,19 @@ __global__ void __launch_bounds__(EV_T, GLIO_EVAL_MINBLOCKS) k_eval_unary(const 
     __threadfence();
     for (int o = threadIdx.x; o < W * NACC; o += EV_T) {
       const int kf = o / NACC, k = o - kf * NACC;
+      // same left-to-right order as a plain loop, but eight independent L2 loads in flight at a time: this tail is a serial
+      // chain of ~15 dependent loads per output otherwise (the last block runs alone on the GPU)
       double v = 0.0;
-      for (int b = kf_item_start[kf]; b < kf_item_start[kf + 1]; ++b) v += partials[(size_t)b * NACC + k];
+      int b = kf_item_start[kf];
+      const int b1 = kf_item_start[kf + 1];
+      for (; b + 8 <= b1; b += 8) {
+        double p[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) p[u] = __ldcg(&partials[(size_t)(b + u) * NACC + k]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v += p[u];
+      }
+      for (; b < b1; ++b) v += __ldcg(&partials[(size_t)b * NACC + k]);
       out[o] = v;
     }
     // `out` may be host-mapped pinned memory: publish the W x NACC doubles system-wide, then raise the epoch flag the
@@ -366,8 +377,19 @@ __global__ void __launch_bounds__(EV_T) k_eval_edge(const EdgeItem* __restrict__
     __threadfence();
     for (int o = threadIdx.x; o < W * NACC; o += EV_T) {
       const int kf = o / NACC, k = o - kf * NACC;
+      // same left-to-right order as a plain loop, but eight independent L2 loads in flight at a time: this tail is a serial
+      // chain of ~15 dependent loads per output otherwise (the last block runs alone on the GPU)
       double v = 0.0;
-      for (int b = kf_item_start[kf]; b < kf_item_start[kf + 1]; ++b) v += partials[(size_t)b * NACC + k];
+      int b = kf_item_start[kf];
+      const int b1 = kf_item_start[kf + 1];
+      for (; b + 8 <= b1; b += 8) {
+        double p[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) p[u] = __ldcg(&partials[(size_t)(b + u) * NACC + k]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v += p[u];
+      }
+      for (; b < b1; ++b) v += __ldcg(&partials[(size_t)b * NACC + k]);
       out[o] = v;
     }
     if (threadIdx.x == 0) *ticket = 0u;

@@ -155,7 +155,7 @@ def test_integrated_marginalisation_two_windows(oracle):
         for win in range(2):
             ks = list(range(win, win + W))
             poses0 = P["poses_init"][ks]; sb0 = sb[ks]
-            s2 = dict(prior=(0,) + spec["prior"][1:] if win == 0 else None, between=[(i - win, j - win) + rest for (i, j, *rest) in spec["between"] if win <= i and j < win + W])
+            s2 = dict(prior=(0,) + spec["prior"][1:] if win == 0 else None, between=[(i - win, j - win) + tuple(rest) for (i, j, *rest) in spec["between"] if win <= i and j < win + W])
             s2["between"] = [tuple(b) for b in s2["between"]]
             hf = api.HostFactorSet()
             if s2["prior"] is not None:
