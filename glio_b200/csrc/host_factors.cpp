@@ -35,11 +35,12 @@ inline void At_skew(const double A[9], const double v[3], double s, double M[9])
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double a = 0; for (int k = 0; k < 3; ++k) a += A[3 * k + i] * S[3 * k + j]; M[3 * i + j] = s * a; }
 }
 
-struct DenseAdder { double* H; int n; inline void operator()(int i, int j, double v) const { H[(size_t)i * n + j] += v; } };
+struct DenseAdder { static constexpr bool lower_only = false; double* H; int n; inline void operator()(int i, int j, double v) const { H[(size_t)i * n + j] += v; } };
 // lower-band storage (solver.h BandMat): only i >= j is stored
 // A non-zero contribution outside the declared half bandwidth is an ERROR (a wrong band would silently give a wrong J^T J):
 // it raises *dropped, and the evaluation fails.
 struct BandAdder {
+  static constexpr bool lower_only = true;            // only i >= j is stored: callers skip the upper triangle
   double* a; int hb; int* dropped;
   inline void operator()(int i, int j, double v) const {
     if (i < j) return;
@@ -63,7 +64,8 @@ inline void accumulate(int m, const double* r, int nb, const int* off, const int
       }
     for (int i = 0; i < nz; ++i) {
       g[col[i]] += val[i] * r[k];
-      for (int j = 0; j < nz; ++j) add(col[i], col[j], val[i] * val[j]);
+      if (Adder::lower_only) { for (int j = 0; j < nz; ++j) if (col[j] <= col[i]) add(col[i], col[j], val[i] * val[j]); }
+      else for (int j = 0; j < nz; ++j) add(col[i], col[j], val[i] * val[j]);
     }
   }
 }
@@ -168,7 +170,7 @@ static int hf_evaluate_impl(void* user, int W, const double* poses, const double
     if (sb) for (int k = 0; k < 9; ++k) r[6 + k] = f.sw[6 + k] * (speed_bias[9 * f.kf + k] - f.sb0[k]);
     for (int k = 0; k < 15; ++k) c += 0.5 * r[k] * r[k];
     if (want_jac) {
-      std::vector<double> J((size_t)15 * nt, 0.0);
+      double J[15 * 15]; std::memset(J, 0, sizeof(double) * 15 * nt);
       for (int k = 0; k < 3; ++k) J[(size_t)k * nt + k] = f.sw[k];
       for (int col = 0; col < 3; ++col) {     // d/d delta: 2 vec(q0c (x) (0,e_col) (x) q)
         double ek[4] = {0, 0, 0, 0}; ek[1 + col] = 1.0;
@@ -176,7 +178,7 @@ static int hf_evaluate_impl(void* user, int W, const double* poses, const double
         for (int k = 0; k < 3; ++k) J[(size_t)(3 + k) * nt + 3 + col] = f.sw[3 + k] * 2.0 * b[1 + k];
       }
       if (sb) for (int k = 0; k < 9; ++k) J[(size_t)(6 + k) * nt + 6 + k] = f.sw[6 + k];
-      const int off[1] = {nt * f.kf}, width[1] = {nt}; const double* Jp[1] = {J.data()};
+      const int off[1] = {nt * f.kf}, width[1] = {nt}; const double* Jp[1] = {J};
       accumulate(15, r, 1, off, width, Jp, add, g);
     }
   }
@@ -199,7 +201,8 @@ static int hf_evaluate_impl(void* user, int W, const double* poses, const double
     for (int k = 0; k < 6; ++k) r[9 + k] = f.sw[9 + k] * (sj[3 + k] - si[3 + k]);
     for (int k = 0; k < 15; ++k) c += 0.5 * r[k] * r[k];
     if (want_jac) {
-      std::vector<double> Ji((size_t)15 * nt, 0.0), Jj((size_t)15 * nt, 0.0);
+      double Ji[15 * 15], Jj[15 * 15];                  // nt <= 15: on the stack (this loop runs once per keyframe per evaluation)
+      std::memset(Ji, 0, sizeof(double) * 15 * nt); std::memset(Jj, 0, sizeof(double) * 15 * nt);
       double M[9];
       // position rows
       for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {
@@ -223,7 +226,7 @@ static int hf_evaluate_impl(void* user, int W, const double* poses, const double
         if (sb) { Ji[(size_t)(6 + a) * nt + 6 + b] = -f.sw[6 + a] * RiT; Jj[(size_t)(6 + a) * nt + 6 + b] = f.sw[6 + a] * RiT; }
       }
       if (sb) for (int k = 0; k < 6; ++k) { Ji[(size_t)(9 + k) * nt + 9 + k] = -f.sw[9 + k]; Jj[(size_t)(9 + k) * nt + 9 + k] = f.sw[9 + k]; }
-      const int off[2] = {nt * f.i, nt * f.j}, width[2] = {nt, nt}; const double* Jp[2] = {Ji.data(), Jj.data()};
+      const int off[2] = {nt * f.i, nt * f.j}, width[2] = {nt, nt}; const double* Jp[2] = {Ji, Jj};
       accumulate(15, r, 2, off, width, Jp, add, g);
     }
   }

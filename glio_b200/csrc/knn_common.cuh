@@ -74,7 +74,127 @@ __device__ __forceinline__ void store_top5(const SearchArgs& a, int64_t p, const
   }
 }
 
+
+// ---- per-thread scanning helpers shared by the box-growth kernels (assoc.cu k_knn_box, knn_tile.cu k_knn_box_start / k_knn_grow)
+__device__ __forceinline__ void scan_range_keys(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz, Top5& t, float& d4f) {
+  for (int k = s; k < e; ++k) {
+    const float4 p = __ldg(&pts[k]);
+    const float d = l2_simple(qx, qy, qz, p.x, p.y, p.z);
+    if (d <= d4f) {                                  // cheap float test first; ties on distance resolved on the full key
+      const unsigned long long key = make_key(d, __float_as_int(p.w));
+      if (key < t.k4) { t.k4 = key; GLIO_KSWAP(t.k3, t.k4) GLIO_KSWAP(t.k2, t.k3) GLIO_KSWAP(t.k1, t.k2) GLIO_KSWAP(t.k0, t.k1) d4f = key_dist(t.k4); }
+    }
+  }
+}
+
+// rings [r_lo, r_hi] of one query's search box; returns true when the top-5 is final (proven inside the scanned box,
+// the box covers the grid, or it covers the gate radius) and false when more rings are needed
+__device__ __forceinline__ bool thread_rings(const GridDesc& g, float qx, float qy, float qz, int cx, int cy, int cz, int r_lo, int r_hi, int rmax,
+                                             Top5& t, float& d4f, int* __restrict__ sb = nullptr) {
+  const float INF = __int_as_float(0x7f800000);
+  const int* __restrict__ cs = g.cell_start;
+  for (int r = r_lo; r <= r_hi; ++r) {
+    const int xa = cx - r, xb = cx + r;
+    const int x0 = max(xa, 0), x1 = min(xb, g.nx - 1);
+    if (r == 1 && sb) {
+      // first ring: fetch the bounds of all nine rows up front (18 independent loads in flight instead of nine
+      // dependent load -> scan steps), park them in this thread's shared-memory column, then scan the query's own
+      // row first so the 5th distance tightens early
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int z = cz + i / 3 - 1, y = cy + i % 3 - 1;
+        int s = 0, e = 0;
+        if (z >= 0 && z < g.nz && y >= 0 && y < g.ny && x0 <= x1) { const int row = (z * g.ny + y) * g.nx; s = __ldg(&cs[row + x0]); e = __ldg(&cs[row + x1 + 1]); }
+        sb[(2 * i) * 128] = s; sb[(2 * i + 1) * 128] = e;
+      }
+#pragma unroll 1
+      for (int i = 0; i < 9; ++i) {
+        const int o = (int)((0x862053714ull >> (4 * i)) & 15ull);     // 4,1,7,3,5,0,2,6,8
+        scan_range_keys(g.pts, sb[(2 * o) * 128], sb[(2 * o + 1) * 128], qx, qy, qz, t, d4f);
+      }
+    } else {
+      const int z0 = max(cz - r, 0), z1 = min(cz + r, g.nz - 1);
+      const int y0 = max(cy - r, 0), y1 = min(cy + r, g.ny - 1);
+      for (int z = z0; z <= z1; ++z) {
+        const bool zshell = (z == cz - r) || (z == cz + r);
+        for (int y = y0; y <= y1; ++y) {
+          const int row = (z * g.ny + y) * g.nx;
+          const bool shell = r == 1 || zshell || (y == cy - r) || (y == cy + r);
+          if (shell) {
+            if (x0 <= x1) scan_range_keys(g.pts, __ldg(&cs[row + x0]), __ldg(&cs[row + x1 + 1]), qx, qy, qz, t, d4f);
+          } else {
+            if (xa >= 0 && xa < g.nx) scan_range_keys(g.pts, __ldg(&cs[row + xa]), __ldg(&cs[row + xa + 1]), qx, qy, qz, t, d4f);
+            if (xb >= 0 && xb < g.nx) scan_range_keys(g.pts, __ldg(&cs[row + xb]), __ldg(&cs[row + xb + 1]), qx, qy, qz, t, d4f);
+          }
+        }
+      }
+    }
+    float b = INF;
+    if (cx - r > 0)        b = fminf(b, qx - (g.ox + (float)(cx - r) * g.cell));
+    if (cx + r < g.nx - 1) b = fminf(b, (g.ox + (float)(cx + r + 1) * g.cell) - qx);
+    if (cy - r > 0)        b = fminf(b, qy - (g.oy + (float)(cy - r) * g.cell));
+    if (cy + r < g.ny - 1) b = fminf(b, (g.oy + (float)(cy + r + 1) * g.cell) - qy);
+    if (cz - r > 0)        b = fminf(b, qz - (g.oz + (float)(cz - r) * g.cell));
+    if (cz + r < g.nz - 1) b = fminf(b, (g.oz + (float)(cz + r + 1) * g.cell) - qz);
+    if (b == INF) return true;
+    const float bs = b * 0.999f - 2e-3f;
+    if (bs > 0.f && key_dist(t.k4) <= bs * bs) return true;
+  }
+  return r_hi >= rmax;
+}
+
+__device__ __forceinline__ void scan_rows(const GridDesc& g, int x0, int x1, int y0, int y1, int z0, int z1, float qx, float qy, float qz, Top5& t, float& d4f) {
+  x0 = max(x0, 0); x1 = min(x1, g.nx - 1); y0 = max(y0, 0); y1 = min(y1, g.ny - 1); z0 = max(z0, 0); z1 = min(z1, g.nz - 1);
+  if (x0 > x1) return;
+  const int* __restrict__ cs = g.cell_start;
+  for (int z = z0; z <= z1; ++z)
+    for (int y = y0; y <= y1; ++y) {
+      const int row = (z * g.ny + y) * g.nx;
+      scan_range_keys(g.pts, __ldg(&cs[row + x0]), __ldg(&cs[row + x1 + 1]), qx, qy, qz, t, d4f);
+    }
+}
+
+
+// one face test of the box growth: does something nearer than the current 5th distance possibly hide beyond face f?
+__device__ __forceinline__ bool box_face_open(const GridDesc& g, int f, float qx, float qy, float qz, float gate_r, int lx, int hx, int ly, int hy, int lz, int hz,
+                                              const Top5& t) {
+  const int ax = f >> 1;
+  const bool up = (f & 1) != 0;
+  const int lo = ax == 0 ? lx : (ax == 1 ? ly : lz), hi = ax == 0 ? hx : (ax == 1 ? hy : hz), n = ax == 0 ? g.nx : (ax == 1 ? g.ny : g.nz);
+  const float qa = ax == 0 ? qx : (ax == 1 ? qy : qz), oa = ax == 0 ? g.ox : (ax == 1 ? g.oy : g.oz);
+  if (up ? (hi >= n - 1) : (lo <= 0)) return false;                   // nothing beyond this face
+  const float b = up ? (oa + (float)(hi + 1) * g.cell) - qa : qa - (oa + (float)lo * g.cell);
+  const float bs = b * 0.999f - 2e-3f;
+  if (bs >= gate_r) return false;                                     // beyond the gate radius
+  if (bs > 0.f && key_dist(t.k4) <= bs * bs) return false;            // the 5th distance is inside this face
+  return true;
+}
+// face-by-face growth of the searched box [lx,hx] x [ly,hy] x [lz,hz] until no face is open (see k_knn_box)
+__device__ __forceinline__ void box_grow(const GridDesc& g, float qx, float qy, float qz, float gate_r, int rmax, int lx, int hx, int ly, int hy, int lz, int hz,
+                                         Top5& t, float& d4f) {
+  for (int round = 0; round < rmax + 3; ++round) {
+    bool any = false;
+#pragma unroll 1
+    for (int f = 0; f < 6; ++f) {
+      if (!box_face_open(g, f, qx, qy, qz, gate_r, lx, hx, ly, hy, lz, hz, t)) continue;
+      const int ax = f >> 1;
+      const bool up = (f & 1) != 0;
+      const int hi = ax == 0 ? hx : (ax == 1 ? hy : hz), lo = ax == 0 ? lx : (ax == 1 ? ly : lz);
+      const int nc = up ? hi + 1 : lo - 1;
+      int bx0 = lx, bx1 = hx, by0 = ly, by1 = hy, bz0 = lz, bz1 = hz;
+      if (ax == 0) { bx0 = bx1 = nc; if (up) hx = nc; else lx = nc; }
+      else if (ax == 1) { by0 = by1 = nc; if (up) hy = nc; else ly = nc; }
+      else { bz0 = bz1 = nc; if (up) hz = nc; else lz = nc; }
+      scan_rows(g, bx0, bx1, by0, by1, bz0, bz1, qx, qy, qz, t, d4f);
+      any = true;
+    }
+    if (!any) break;
+  }
+}
+
 // K1a, staged tile search + team pass (knn_tile.cu, GLIO_KNN_MODE=4)
 void knn_tile_run(const SearchArgs& sa, const PairRec* d_pairs, DevBuf<int>& work, DevBuf<int>& scan_tmp, cudaStream_t st, LaunchCounter& lc);
+// K1a, box search split in two launches (GLIO_KNN_MODE=5): start box for everyone, face growth for the compacted rest
+void knn_box2_run(const SearchArgs& sa, DevBuf<int>& work, DevBuf<int>& scan_tmp, cudaStream_t st, LaunchCounter& lc);
 
 }  // namespace glio

@@ -488,4 +488,82 @@ void knn_tile_run(const SearchArgs& sa, const PairRec* d_pairs, DevBuf<int>& wor
   GLIO_CUDA_TRY(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// GLIO_KNN_MODE=5: the per-thread box search of assoc.cu (k_knn_box) split in two launches.  In the fused kernel the face
+// growth runs at about 5 of 32 lanes (one query in ten needs it, each warp waits for its few growing lanes) and costs two
+// fifths of all instructions; here the first launch stops after the 3x3x3 start box, the queries with an open face are
+// compacted IN SORTED ORDER (k_defer_scatter), and the second launch grows them with every lane busy.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 6) k_knn_box_start(TileArgs ta) {
+  __shared__ int sbnd[18 * 128];
+  const SearchArgs& a = ta.sa;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const GridDesc& g = a.grid;
+  bool open = false;
+  if (p < a.Qt) {
+    const float4 q4 = a.pm[a.order[p]];
+    const float qx = q4.x, qy = q4.y, qz = q4.z;
+    Top5 t; top5_init(t);
+    const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
+    const float gate_r = sqrtf(a.gate_sq) + 2e-3f;
+    const int rmax = (int)ceilf(gate_r * g.inv_cell) + 1;
+    const bool far_out = cx < -rmax || cy < -rmax || cz < -rmax || cx >= g.nx + rmax || cy >= g.ny + rmax || cz >= g.nz + rmax;
+    float d4f = __int_as_float(0x7f800000);
+    if (!far_out) {
+      thread_rings(g, qx, qy, qz, cx, cy, cz, 1, 1, rmax, t, d4f, sbnd + threadIdx.x);
+#pragma unroll 1
+      for (int f = 0; f < 6 && !open; ++f) open = box_face_open(g, f, qx, qy, qz, gate_r, cx - 1, cx + 1, cy - 1, cy + 1, cz - 1, cz + 1, t);
+    }
+    // the second launch rebuilds the keys from all five (index, distance) pairs
+    a.knn_idx[0 * a.Qt + p] = key_idx(t.k0); a.knn_idx[1 * a.Qt + p] = key_idx(t.k1); a.knn_idx[2 * a.Qt + p] = key_idx(t.k2);
+    a.knn_idx[3 * a.Qt + p] = key_idx(t.k3); a.knn_idx[4 * a.Qt + p] = key_idx(t.k4);
+    a.knn_sqd[4 * a.Qt + p] = key_dist(t.k4);
+    if (open || a.store_all_sqd) {
+      a.knn_sqd[0 * a.Qt + p] = key_dist(t.k0); a.knn_sqd[1 * a.Qt + p] = key_dist(t.k1); a.knn_sqd[2 * a.Qt + p] = key_dist(t.k2);
+      a.knn_sqd[3 * a.Qt + p] = key_dist(t.k3);
+    }
+  }
+  const unsigned dm = __ballot_sync(0xffffffffu, open);
+  const int gw = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (lane == 0) { ta.dmask[gw] = dm; ta.dcount[gw] = __popc(dm); }
+}
+
+__global__ void __launch_bounds__(128, 6) k_knn_grow(TileArgs ta) {
+  const SearchArgs& a = ta.sa;
+  const GridDesc& g = a.grid;
+  const unsigned int nd = (unsigned int)ta.dpos[ta.nwarps];
+  const float gate_r = sqrtf(a.gate_sq) + 2e-3f;
+  const int rmax = (int)ceilf(gate_r * g.inv_cell) + 1;
+  for (unsigned int item = blockIdx.x * blockDim.x + threadIdx.x; item < nd; item += gridDim.x * blockDim.x) {
+    const int64_t p = a.deferred[item];
+    const float4 q4 = a.pm[a.order[p]];
+    const float qx = q4.x, qy = q4.y, qz = q4.z;
+    const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
+    Top5 t;
+    t.k0 = make_key(a.knn_sqd[0 * a.Qt + p], a.knn_idx[0 * a.Qt + p]); t.k1 = make_key(a.knn_sqd[1 * a.Qt + p], a.knn_idx[1 * a.Qt + p]);
+    t.k2 = make_key(a.knn_sqd[2 * a.Qt + p], a.knn_idx[2 * a.Qt + p]); t.k3 = make_key(a.knn_sqd[3 * a.Qt + p], a.knn_idx[3 * a.Qt + p]);
+    t.k4 = make_key(a.knn_sqd[4 * a.Qt + p], a.knn_idx[4 * a.Qt + p]);
+    float d4f = key_dist(t.k4);
+    box_grow(g, qx, qy, qz, gate_r, rmax, cx - 1, cx + 1, cy - 1, cy + 1, cz - 1, cz + 1, t, d4f);
+    store_top5(a, p, t);
+  }
+}
+
+void knn_box2_run(const SearchArgs& sa, DevBuf<int>& work, DevBuf<int>& scan_tmp, cudaStream_t st, LaunchCounter& lc) {
+  const unsigned nb = (unsigned)((sa.Qt + 127) / 128);
+  const int nw = (int)nb * 4;
+  work.reserve((size_t)3 * nw + 8);
+  TileArgs ta;
+  ta.sa = sa; ta.pairs = nullptr; ta.nwarps = nw;
+  ta.dmask = reinterpret_cast<unsigned int*>(work.p); ta.dcount = work.p + nw; ta.dpos = work.p + 2 * nw + 1;
+  ta.n_fb = nullptr; ta.fb_list = nullptr;
+  GLIO_CUDA_TRY(cudaMemsetAsync(ta.dcount + nw, 0, sizeof(int), st));
+  lc.begin("k_knn_box_start", st); k_knn_box_start<<<nb, 128, 0, st>>>(ta); lc.end(st);
+  exclusive_scan_i32(ta.dcount, work.p + 2 * nw + 1, (int64_t)nw + 1, scan_tmp, st, lc);
+  lc.begin("k_defer_scatter", st); k_defer_scatter<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(ta); lc.end(st);
+  lc.begin("k_knn_grow", st); k_knn_grow<<<148 * 12, 128, 0, st>>>(ta); lc.end(st);
+  GLIO_CUDA_TRY(cudaGetLastError());
+}
+
 }  // namespace glio
