@@ -5,14 +5,15 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs use it, and there only as the checker / the reported CPU baseline.
  *
- * PARITY UNPINNED: the reference (XikunLiu-huskit/GLIO @ 332d19ff) ships no tests,
- * golden vectors or fixtures for this path, and it cannot be compiled in this image
- * (no Eigen / Ceres install / PCL / FLANN / ROS).  The oracle is therefore authored from the
- * reference *source* and from the published algorithms of its absent dependencies
- * (Eigen 3.3.4 ColPivHouseholderQR / Quaternion, FLANN 1.9 L2_Simple<float>
- * KDTreeSingleIndex, Ceres 2.0.0 whose source IS vendored as a tarball), and is pinned
- * only by (i) Ceres' own known-answer tests transcribed in tests/, (ii) analytic
- * planted-plane fixtures, (iii) an independent numpy/scipy cross-check.
+ * PARITY STATUS: the reference (XikunLiu-huskit/GLIO @ 332d19ff) ships no tests, golden vectors or fixtures for this
+ * path, and it cannot be compiled in this image (no Eigen / Ceres install / PCL / ROS), so there is no oracle/_ref.
+ * The oracle is authored from the reference *source* and from the published algorithms of its absent dependencies
+ * (Eigen 3.3.4 ColPivHouseholderQR / Quaternion, FLANN 1.9 L2_Simple<float> KDTreeSingleIndex, PCL VoxelGrid, Ceres
+ * 2.0.0 whose source IS vendored as a tarball).  PINNED (tests/test_oracle_pins.py, test_oracle_known_answers.py,
+ * tests/cpp/*): the kNN bit for bit to OpenCV's bundled FLANN (KDTREE_SINGLE and LINEAR, also at M = 1 M), the 5x3 plane
+ * solve to LAPACK's pivoted QR, the Ceres pieces (corrector, loss, quaternion parameterization, dogleg, Levenberg-Marquardt,
+ * Powell, polynomial roots) to Ceres' own known-answer tests.  PARITY UNPINNED for what no library in the image can check:
+ * pcl::VoxelGrid, Eigen's packet-order reductions, std::sort's tie order (VoxelGrid, feature extraction).
  *
  * Every function cites the reference file:line it follows.  Paths are relative to
  * /root/reference; "ceres.tgz::" means support_files/ceres-solver.tar.gz → ceres-solver/.
