@@ -390,7 +390,7 @@ int glio_create(int device, const glio_params* params, glio_ctx** out) {
     c = new glio_ctx();
     c->device = device;
     if (params) c->prm = *params; else glio_default_params(&c->prm);
-    if (const char* e = getenv("GLIO_KNN_MODE")) { const int v = atoi(e); if (v >= 0 && v <= 5) c->knn_mode = v; }
+    if (const char* e = getenv("GLIO_KNN_MODE")) { const int v = atoi(e); if (v >= 0 && v <= 6) c->knn_mode = v; }
     if (const char* e = getenv("GLIO_TILE_RINGS")) { const int v = atoi(e); if (v >= 1 && v < 64) c->tile_rings = v; }
     if (const char* e = getenv("GLIO_PTS_PER_CELL")) { const float v = (float)atof(e); if (v > 0.1f && v < 1000.f) c->pts_per_cell = v; }
     c->map.build_pairs = c->knn_mode == 4;

@@ -566,4 +566,52 @@ void knn_box2_run(const SearchArgs& sa, DevBuf<int>& work, DevBuf<int>& scan_tmp
   GLIO_CUDA_TRY(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// GLIO_KNN_MODE=6: k_knn_box, except that a query with fewer than five map points in its 3x3x3 start box (it lies far from
+// every surface: its result needs the whole gate sphere, about 700 cells scanned one row after the other by one thread) is
+// handed to the team pass, where several lanes share that scan.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 6) k_knn_box_far(SearchArgs a) {
+  __shared__ int sbnd[18 * 128];
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const GridDesc& g = a.grid;
+  bool far = false;
+  if (p < a.Qt) {
+    const float4 q4 = a.pm[a.order[p]];
+    const float qx = q4.x, qy = q4.y, qz = q4.z;
+    Top5 t; top5_init(t);
+    const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
+    const float gate_r = sqrtf(a.gate_sq) + 2e-3f;
+    const int rmax = (int)ceilf(gate_r * g.inv_cell) + 1;
+    const bool far_out = cx < -rmax || cy < -rmax || cz < -rmax || cx >= g.nx + rmax || cy >= g.ny + rmax || cz >= g.nz + rmax;
+    float d4f = __int_as_float(0x7f800000);
+    if (!far_out) {
+      thread_rings(g, qx, qy, qz, cx, cy, cz, 1, 1, rmax, t, d4f, sbnd + threadIdx.x);
+      far = key_idx(t.k4) == 0x7fffffff;
+      if (far) {
+        bool open = false;
+#pragma unroll 1
+        for (int f = 0; f < 6 && !open; ++f) open = box_face_open(g, f, qx, qy, qz, gate_r, cx - 1, cx + 1, cy - 1, cy + 1, cz - 1, cz + 1, t);
+        far = open;                                   // a box already clipped by the grid on every side is final as it is
+      }
+      if (!far) box_grow(g, qx, qy, qz, gate_r, rmax, cx - 1, cx + 1, cy - 1, cy + 1, cz - 1, cz + 1, t, d4f);
+    }
+    store_top5(a, p, t);                              // far: knn_sqd[4] = +inf -> the team pass searches the gate sphere
+  }
+  const unsigned fm = __ballot_sync(0xffffffffu, far);
+  if (fm) {
+    unsigned int base = 0;
+    if (lane == 0) { base = atomicAdd(a.n_deferred, (unsigned int)__popc(fm)); if (a.n_fallback) atomicAdd(a.n_fallback, (unsigned long long)__popc(fm)); }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (far) a.deferred[base + __popc(fm & ((1u << lane) - 1u))] = (uint32_t)p;
+  }
+}
+
+void knn_box_far_run(const SearchArgs& sa, cudaStream_t st, LaunchCounter& lc) {
+  lc.begin("k_knn_box_far", st); k_knn_box_far<<<(unsigned)((sa.Qt + 127) / 128), 128, 0, st>>>(sa); lc.end(st);
+  lc.begin("k_knn_team", st); k_knn_team<<<148 * 12, 128, 0, st>>>(sa, sa.deferred, sa.n_deferred); lc.end(st);
+  GLIO_CUDA_TRY(cudaGetLastError());
+}
+
 }  // namespace glio
