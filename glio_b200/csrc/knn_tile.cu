@@ -608,9 +608,149 @@ __global__ void __launch_bounds__(128, 6) k_knn_box_far(SearchArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_knn_far: one WARP per far query (fewer than five map points in its start box, so the whole gate sphere has to be
+// searched).  Lanes own the cell rows of the sphere's bounding box for the bounds (two loads per row, 32 rows at a time,
+// each row clipped to the circle the sphere cuts out of it), then the candidates of those rows are FLATTENED over the lanes
+// (warp scan of the row lengths, per-lane binary search by shuffle) so every lane evaluates one candidate per step whatever
+// the rows look like.  Pass A: per-lane minimum of the exact distances; the 5th smallest of the 32 lane minima bounds the 5th
+// neighbour distance (five distinct candidates).  Pass B: candidates under the bound are collected (ballot + prefix) into a
+// small shared list; the five smallest (distance, index) keys of the list are extracted with warp reductions.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int FAR_WARPS = 4;
+constexpr int FAR_ROWS = 512;        // rows of the bounding box kept per warp ((2R+1)^2 with R = ceil(gate radius / cell) <= 11)
+constexpr int FAR_LIST = 128;        // survivor list capacity
+
+__device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k) {
+  const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(k >> 32));
+  const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(k >> 32) == hi ? (unsigned)k : 0xffffffffu);
+  return ((unsigned long long)hi << 32) | lo;
+}
+
+__global__ void __launch_bounds__(32 * FAR_WARPS) k_knn_far(SearchArgs a, const uint32_t* __restrict__ qlist, const unsigned int* __restrict__ n_list) {
+  __shared__ int s_rs[FAR_WARPS][FAR_ROWS];            // first point of the row's range
+  __shared__ int s_rl[FAR_WARPS][FAR_ROWS];            // its length
+  __shared__ unsigned long long s_keys[FAR_WARPS][FAR_LIST];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned int nwarps = gridDim.x * FAR_WARPS;
+  const unsigned int nd = *n_list;
+  const GridDesc& G = a.grid;
+  const int* __restrict__ cs = G.cell_start;
+  const float INF = __int_as_float(0x7f800000);
+  const float T0 = a.gate_sq * TK_MARGIN;              // nothing beyond the radius gate can matter (Estimator.cpp:3651)
+  int* rs = s_rs[wid]; int* rl = s_rl[wid];
+  unsigned long long* keys = s_keys[wid];
+  for (unsigned int item = blockIdx.x * FAR_WARPS + wid; item < nd; item += nwarps) {
+    const int64_t p = qlist[item];
+    const float4 q4 = a.pm[a.order[p]];
+    const float qx = q4.x, qy = q4.y, qz = q4.z;
+    const float r = sqrtf(T0) * 1.001f + 2e-3f;
+    const int ylo = max(cell_coord(qy - r, G.oy, G.inv_cell), 0), yhi = min(cell_coord(qy + r, G.oy, G.inv_cell), G.ny - 1);
+    const int zlo = max(cell_coord(qz - r, G.oz, G.inv_cell), 0), zhi = min(cell_coord(qz + r, G.oz, G.inv_cell), G.nz - 1);
+    const int nyr = yhi - ylo + 1, nzr = zhi - zlo + 1;
+    const int nrows_all = (nyr > 0 && nzr > 0) ? nyr * nzr : 0;
+    float bound = T0;
+    unsigned long long best[5] = {KEY_EMPTY, KEY_EMPTY, KEY_EMPTY, KEY_EMPTY, KEY_EMPTY};
+    int nlist = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      float lane_min = INF;
+#pragma unroll 1
+      for (int row0 = 0; row0 < nrows_all; row0 += FAR_ROWS) {          // (one window unless the cells are tiny)
+        const int nrows = min(nrows_all - row0, FAR_ROWS);
+        // ---- bounds of every row of the window, clipped to the circle the sphere cuts out of the row
+        __syncwarp();
+        for (int ri = lane; ri < nrows; ri += 32) {
+          const int z = zlo + (row0 + ri) / nyr, y = ylo + (row0 + ri) % nyr;
+          const float yl = G.oy + (float)y * G.cell, zl = G.oz + (float)z * G.cell;
+          const float dy = fmaxf(fmaxf(yl - qy, qy - (yl + G.cell)), 0.f), dz = fmaxf(fmaxf(zl - qz, qz - (zl + G.cell)), 0.f);
+          const float dys = fmaxf(dy * 0.999f - 2e-3f, 0.f), dzs = fmaxf(dz * 0.999f - 2e-3f, 0.f);
+          const float rem = T0 - (dys * dys + dzs * dzs);
+          int s = 0, len = 0;
+          if (rem >= 0.f) {
+            const float rx = sqrtf(rem) * 1.001f + 2e-3f;
+            const int xl = max(cell_coord(qx - rx, G.ox, G.inv_cell), 0), xh = min(cell_coord(qx + rx, G.ox, G.inv_cell), G.nx - 1);
+            if (xl <= xh) { const int row = (z * G.ny + y) * G.nx; s = __ldg(&cs[row + xl]); len = __ldg(&cs[row + xh + 1]) - s; }
+          }
+          rs[ri] = s; rl[ri] = len;
+        }
+        __syncwarp();
+        for (int rb = 0; rb < nrows; rb += 32) {
+          const int ri = rb + lane;
+          const int len = ri < nrows ? rl[ri] : 0, s = ri < nrows ? rs[ri] : 0;
+          int incl = len;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+          const int total = __shfl_sync(0xffffffffu, incl, 31);
+          for (int base = 0; base < total; base += 32) {
+            const int c = base + lane;
+            // row of flat candidate c: the first lane whose inclusive count exceeds c (binary search over the lanes by shuffle)
+            int lo = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) { const int v = __shfl_sync(0xffffffffu, incl, lo + step - 1); if (v <= c) lo += step; }
+            const int src_incl = __shfl_sync(0xffffffffu, incl, lo), src_len = __shfl_sync(0xffffffffu, len, lo), src_s = __shfl_sync(0xffffffffu, s, lo);
+            float d = INF; int id = 0x7fffffff;
+            if (c < total) {
+              const float4 pt = __ldg(&G.pts[src_s + (c - (src_incl - src_len))]);
+              d = l2_simple(qx, qy, qz, pt.x, pt.y, pt.z); id = __float_as_int(pt.w);
+            }
+            if (pass == 0) lane_min = fminf(lane_min, d);
+            else {
+              const bool keep = d <= bound;
+              const unsigned bm = __ballot_sync(0xffffffffu, keep);
+              if (keep) { const int slot = nlist + __popc(bm & ((1u << lane) - 1u)); if (slot < FAR_LIST) keys[slot] = make_key(d, id); else top5_push(*reinterpret_cast<Top5*>(best), d, id); }
+              nlist = min(nlist + __popc(bm), FAR_LIST + 64);
+            }
+          }
+        }
+      }
+      if (pass == 0) {
+        // 5th smallest of the 32 lane minima (each is a distinct candidate); fewer than five finite minima leave the gate as the bound
+        unsigned mine = __float_as_uint(lane_min), fifth = 0x7f800000u;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const unsigned m = __reduce_min_sync(0xffffffffu, mine);
+          fifth = m;
+          const unsigned who = __ballot_sync(0xffffffffu, mine == m);
+          if (lane == __ffs(who) - 1) mine = 0x7f800000u;
+        }
+        bound = fminf(__uint_as_float(fifth), T0);
+      }
+    }
+    __syncwarp();
+    // ---- the five smallest keys of the list (+ anything that overflowed into lane-private `best`, folded in by every lane)
+    Top5 t; top5_init(t);
+    const int nl = min(nlist, FAR_LIST);
+    unsigned long long mykeys[FAR_LIST / 32];
+#pragma unroll
+    for (int u = 0; u < FAR_LIST / 32; ++u) { const int i = u * 32 + lane; mykeys[u] = i < nl ? keys[i] : KEY_EMPTY; }
+    // overflow candidates live in one lane's `best`: bring them into the pool as well
+    unsigned long long ov[5] = {best[0], best[1], best[2], best[3], best[4]};
+    unsigned long long res[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      unsigned long long m = KEY_EMPTY;
+#pragma unroll
+      for (int u = 0; u < FAR_LIST / 32; ++u) m = m < mykeys[u] ? m : mykeys[u];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) m = m < ov[u] ? m : ov[u];
+      const unsigned long long g = warp_min_key(m);
+      res[k] = g;
+      // remove one copy of it (keys are distinct points, so at most one lane slot holds it)
+#pragma unroll
+      for (int u = 0; u < FAR_LIST / 32; ++u) if (mykeys[u] == g) mykeys[u] = KEY_EMPTY;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) if (ov[u] == g) ov[u] = KEY_EMPTY;
+    }
+    t.k0 = res[0]; t.k1 = res[1]; t.k2 = res[2]; t.k3 = res[3]; t.k4 = res[4];
+    if (lane == 0) store_top5(a, p, t);
+    __syncwarp();
+  }
+}
+
 void knn_box_far_run(const SearchArgs& sa, cudaStream_t st, LaunchCounter& lc) {
   lc.begin("k_knn_box_far", st); k_knn_box_far<<<(unsigned)((sa.Qt + 127) / 128), 128, 0, st>>>(sa); lc.end(st);
-  lc.begin("k_knn_team", st); k_knn_team<<<148 * 12, 128, 0, st>>>(sa, sa.deferred, sa.n_deferred); lc.end(st);
+  lc.begin("k_knn_far", st); k_knn_far<<<148 * 8, 32 * FAR_WARPS, 0, st>>>(sa, sa.deferred, sa.n_deferred); lc.end(st);
   GLIO_CUDA_TRY(cudaGetLastError());
 }
 
