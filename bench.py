@@ -430,14 +430,16 @@ def run_glio(args, rank, world, local_rank):
     ctx.lib_profile(False)
 
     # (C) end to end through the C ABI with pinned HOST buffers in the reference's PointXYZI layout.  A sliding window gets ONE
-    #     new keyframe per call: every step uploads the rebuilt local map (32 MB, in line: it depends on the poses the previous
-    #     solve produced, so it cannot be prefetched) and the newest keyframe's scan (3.2 MB, copy stream, handed over right
+    #     new keyframe per call: every step uploads the rebuilt local map (32 MB; it depends on the poses the previous solve
+    #     produced, so its upload can only start when that solve has returned: it runs on the copy stream during the
+    #     marginalisation of the previous window and the rest is waited for in line) and the newest keyframe's scan (3.2 MB, copy stream, handed over right
     #     after the association of the current window - the order a live system has: the next keyframe's cloud arrives while
     #     the current window is optimised); the other W-1 scans are resident, as they are after glio_window_slide.
     def timed_run_e2e(nsteps):
         iters = 0
         ctx.window_set_scans(dscans[1:W + 1])
         ctx.window_set_scan(W - 1, hnew)
+        ctx.map_prefetch(hmap)                      # prologue upload of the first map (outside the timed region, like the first scan)
         if dist is not None:
             dist.barrier()
         ctx.synchronize(); torch.cuda.synchronize()
@@ -451,9 +453,10 @@ def run_glio(args, rank, world, local_rank):
             ctx.window_associate(posesB)
             ctx.window_set_scan(W - 1, hnew)        # next step's new keyframe: asynchronous, copy stream
             r = ctx.window_solve(posesB, sb0, hfB, opts, band=band)
+            ctx.map_prefetch(hmap)                  # the poses are final: the next window's rebuilt map starts its upload (copy stream)
             ctx.window_marginalize(r["poses"], r["speed_bias"], hfB)
             iters += len(r["steps"])
-        ctx.synchronize()                           # both streams: the last upload is inside the timed region too
+        ctx.synchronize()                           # both streams: the last uploads are inside the timed region too
         e1.record(st)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -589,7 +592,7 @@ def run_glio(args, rank, world, local_rank):
                             host_wall_ms_per_step=1e3 * wall / args.steps, ms_per_step_with_kernel_events=ms_prof / args.steps, knn_deferred_queries_per_step=n_fallback / args.steps, wall_split=split,
                             solve_split_ms=dict(total=round(1e3 * s.total_seconds, 3), evaluation=round(1e3 * s.eval_seconds, 3), band_cholesky=round(1e3 * s.linear_solver_seconds, 3)), kernels=kern),
                 e2e=dict(value=e2e, unit="iterations/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=tmax_e / args.steps,
-                         how="pinned host buffers in the PointXYZI layout through the C ABI; per step: the rebuilt local map (32 MB, in line) + the newest keyframe's scan (3.2 MB, copy stream, overlapping this window's solve; the other 19 scans are resident as after glio_window_slide) + per-iteration pose/result traffic; final poses and the prior stay on the host side"),
+                         how="pinned host buffers in the PointXYZI layout through the C ABI; per step: the rebuilt local map (32 MB; upload started when the previous solve has returned, overlapping that window's marginalisation, remainder in line) + the newest keyframe's scan (3.2 MB, copy stream, overlapping this window's solve; the other 19 scans are resident as after glio_window_slide) + per-iteration pose/result traffic; final poses and the prior stay on the host side"),
                 gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu, parity_fullsize=(parity["ok"] if parity else None), parity_detail=parity,
                 batch=batch, microbench=micro)
     print(json.dumps(line))

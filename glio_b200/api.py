@@ -167,6 +167,12 @@ class Context:
         self._map_keep = keep
         self._chk(self._lib.glio_set_map(self._h, p, C.c_int64(n), C.c_int(stride), C.c_int(mem)))
 
+    def map_prefetch(self, xyz):
+        keep, p, n, stride, mem = _points_arg(xyz)
+        assert mem == HOST
+        self._map_pf_keep = keep
+        self._chk(self._lib.glio_map_prefetch(self._h, p, C.c_int64(n), C.c_int(stride)))
+
     # ---- K1
     # ---- local map maintenance on the device
     def localmap_clear(self):

@@ -55,6 +55,8 @@ struct glio_ctx {
   GridBuild map;
   bool has_map = false;
   DevBuf<float> map_stage;
+  // map prefetch (glio_map_prefetch): the next window's local map travels on the copy stream while the current window is marginalised
+  DevBuf<float> map_stage2; const float* pf_ptr = nullptr; int64_t pf_M = 0; int pf_stride = 0; cudaEvent_t ev_map = nullptr;
 
   std::vector<std::unique_ptr<Slot>> slots;
 
@@ -410,7 +412,7 @@ void glio_destroy(glio_ctx* c) {
   cudaSetDevice(c->device);
   if (c->st_copy) cudaStreamSynchronize(c->st_copy);
   if (c->st) cudaStreamSynchronize(c->st);
-  c->map.release(); c->map_stage.release();
+  c->map.release(); c->map_stage.release(); c->map_stage2.release(); if (c->ev_map) cudaEventDestroy(c->ev_map);
   for (auto& f : c->lm_frames) f->pts.release();
   for (auto& f : c->lm_spare) f->pts.release();
   c->lm_frames.clear(); c->lm_spare.clear(); c->lm_stage.release(); c->lm_cat.release(); c->lm_vox.release();
@@ -534,9 +536,30 @@ int glio_set_map(glio_ctx* c, const float* xyz, int64_t M, int stride, int mem) 
   if (!c) return GLIO_ERR_ARG;
   return guarded(c, [&] {
     GLIO_REQUIRE(M >= 5, GLIO_ERR_ARG, "map needs at least 5 points");
-    const float* d = stage_points(c, c->map_stage, xyz, M, stride, mem);
+    const float* d;
+    if (mem != GLIO_DEVICE && c->pf_ptr == xyz && c->pf_M == M && c->pf_stride == stride) {
+      // the upload was started by glio_map_prefetch: wait for it on the main stream, no second copy
+      GLIO_CUDA_TRY(cudaStreamWaitEvent(c->st, c->ev_map, 0));
+      std::swap(c->map_stage, c->map_stage2);
+      d = c->map_stage.p;
+    } else d = stage_points(c, c->map_stage, xyz, M, stride, mem);
+    c->pf_ptr = nullptr;
     grid_build(c->map, d, stride, M, nullptr, nullptr, c->prm.cell_size, c->pts_per_cell, c->st, c->lc);
     c->has_map = true; c->map_n = M;
+  });
+}
+
+// Start the host->device copy of the NEXT local map on the copy stream (returns at once).  A following glio_set_map with the same
+// pointer, count and stride uses the staged copy.  The caller must not modify the host buffer until that glio_set_map.
+int glio_map_prefetch(glio_ctx* c, const float* xyz, int64_t M, int stride) {
+  if (!c) return GLIO_ERR_ARG;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(xyz != nullptr && M >= 5 && stride >= 3 && stride <= 64, GLIO_ERR_ARG, "glio_map_prefetch: bad arguments");
+    if (!c->ev_map) GLIO_CUDA_TRY(cudaEventCreateWithFlags(&c->ev_map, cudaEventDisableTiming));
+    c->map_stage2.reserve((size_t)M * stride);
+    GLIO_CUDA_TRY(cudaMemcpyAsync(c->map_stage2.p, xyz, (size_t)M * stride * sizeof(float), cudaMemcpyHostToDevice, c->st_copy));
+    GLIO_CUDA_TRY(cudaEventRecord(c->ev_map, c->st_copy));
+    c->pf_ptr = xyz; c->pf_M = M; c->pf_stride = stride;
   });
 }
 

@@ -96,6 +96,10 @@ void glio_lidar_pose(const glio_params* prm, const double pose_body[7], double t
 /* ---- K0: local-map upload + uniform-grid build.
  * Replaces kd_tree_surf_local_map->setInputCloud(surf_local_map_ds)  (Estimator.cpp:2056). */
 int glio_set_map(glio_ctx* ctx, const float* xyz, int64_t M, int stride_floats, int mem);
+/* start the upload of the NEXT map from (pinned) host memory on the copy stream and return; the following glio_set_map with the same
+ * pointer / count / stride uses the staged copy.  The poses a map is built from are final when the solve returns, so a caller can
+ * hand the rebuilt map over while the window is still being marginalised. */
+int glio_map_prefetch(glio_ctx* ctx, const float* xyz, int64_t M, int stride_floats);
 
 /* ---- Local map maintenance on the device.
  * Replaces Estimator::buildLocalMapWithLandMark (Estimator.cpp:3529-3610: the deque `recent_surf_keyframes` of

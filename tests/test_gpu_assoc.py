@@ -80,3 +80,21 @@ def test_window_slide_equals_fresh_window(ctx, oracle):
             assert np.array_equal(d[key], snap[k][0][key])
         for key in ("cp", "nsd", "weight", "src"):
             assert np.array_equal(m[key], snap[k][1][key])
+
+
+def test_map_prefetch_equals_inline_upload(ctx, oracle):
+    """glio_map_prefetch + glio_set_map (staged copy, copy stream) gives the association of the in-line upload; a prefetch that
+    does not match the following set_map (other pointer) is ignored."""
+    P = synth.window_problem(W=2, Q=2000, M=30000, seed=29)
+    other = synth.window_problem(W=1, Q=10, M=30000, seed=30)["map_xyz"]
+    ctx.window_set_scans(P["scans"])
+    ctx.set_map(P["map_xyz"])
+    nm0 = ctx.window_associate(P["poses_init"]); d0 = ctx.get_assoc_debug(1, 2000)
+    m = np.ascontiguousarray(P["map_xyz"])
+    ctx.map_prefetch(m); ctx.set_map(m)
+    nm1 = ctx.window_associate(P["poses_init"]); d1 = ctx.get_assoc_debug(1, 2000)
+    ctx.map_prefetch(other); ctx.set_map(m)                 # stale prefetch of another buffer: the in-line path is taken
+    nm2 = ctx.window_associate(P["poses_init"]); d2 = ctx.get_assoc_debug(1, 2000)
+    assert np.array_equal(nm0, nm1) and np.array_equal(nm0, nm2)
+    for k in ("status", "idx5", "sqd5", "plane"):
+        assert np.array_equal(d0[k], d1[k]) and np.array_equal(d0[k], d2[k])
