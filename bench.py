@@ -74,7 +74,7 @@ class ClockSampler:
     many short launches by milliseconds per step."""
 
     def __init__(self, dev_index):
-        self.samples = []; self.reasons = set(); self.max_mhz = None; self.ok = False
+        self.samples = []; self.reasons = set(); self.max_mhz = None; self.ok = False; self.cost_ms = 0.0
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -95,6 +95,7 @@ class ClockSampler:
     def sample(self):
         if not self.ok:
             return
+        t0 = time.perf_counter()
         try:
             nv = self._nv
             self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
@@ -104,13 +105,15 @@ class ClockSampler:
                     self.reasons.add(k)
         except Exception:
             pass
+        self.cost_ms += 1e3 * (time.perf_counter() - t0)
 
     def reset(self):
-        self.samples = []; self.reasons = set()
+        self.samples = []; self.reasons = set(); self.cost_ms = 0.0
 
     def result(self):
         return dict(sm_mhz=float(np.median(self.samples)) if self.samples else None, sm_max_mhz=self.max_mhz,
-                    reasons=sorted(self.reasons), samples=len(self.samples), how="NVML, read inside the timed region at step boundaries")
+                    reasons=sorted(self.reasons), samples=len(self.samples), sampling_cost_ms=round(self.cost_ms, 3),
+                    how="NVML, read inside the timed region at step boundaries (three reads: first, middle, last step); sampling_cost_ms is the host time of those reads, which IS part of the timed region")
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -382,7 +385,7 @@ def run_glio(args, rank, world, local_rank):
 
     def timed_run(nsteps, sampler=None):
         iters = 0
-        every = max(1, (nsteps + 3) // 4)              # ~5 NVML reads per run: one read costs ~0.5 ms of stalled launches on this box
+        marks = {0, nsteps // 2, nsteps - 1}            # three NVML reads per run: a read stalls the launch queue for 0.5 - 4 ms depending on the box
         ctx.window_set_scans(dscans[1:W + 1])
         if dist is not None:
             dist.barrier()
@@ -395,7 +398,7 @@ def run_glio(args, rank, world, local_rank):
                 flush.fill_(1)                      # L2 flush between steps (256 MB > 126 MB L2), inside the timed region
             it, _r, _p = one_step(dmap)
             iters += it
-            if sampler is not None and (si % every == 0 or si == nsteps - 1):
+            if sampler is not None and si in marks:
                 sampler.sample()
         e1.record(st)
         torch.cuda.synchronize()

@@ -67,6 +67,26 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_add(int* __restrict__ out, cons
     if (base + k < n) out[base + k] += add;
 }
 
+// second half of a two-launch scan: every block sums the block totals in front of it by itself (nb <= 4096 totals: one
+// coalesced read + a block reduction) instead of waiting for a third launch to scan them
+__global__ void __launch_bounds__(SCAN_T) k_scan_add2(int* __restrict__ out, const int* __restrict__ block_sums, int64_t n) {
+  __shared__ int warp_sums[32];
+  int part = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x; i += SCAN_T) part += block_sums[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = part;
+  __syncthreads();
+  int add = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_T / 32; ++w) add += warp_sums[w];
+  if (blockIdx.x == 0) return;
+  const int64_t base = (int64_t)blockIdx.x * SCAN_B + (int64_t)threadIdx.x * SCAN_IPT;
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; ++k)
+    if (base + k < n) out[base + k] += add;
+}
+
 static void scan_rec(const int* in, int* out, int64_t n, int* tmp, int64_t tmp_cap, cudaStream_t st, LaunchCounter& lc) {
   const int64_t nb = (n + SCAN_B - 1) / SCAN_B;
   if (nb <= 1) {
@@ -75,6 +95,10 @@ static void scan_rec(const int* in, int* out, int64_t n, int* tmp, int64_t tmp_c
   }
   GLIO_REQUIRE(nb <= tmp_cap, GLIO_ERR_STATE, "scan scratch too small");
   lc.begin("k_scan_block", st); k_scan_block<<<(unsigned)nb, SCAN_T, 0, st>>>(in, out, tmp, n); lc.end(st);
+  if (nb <= 4096) {
+    lc.begin("k_scan_add", st); k_scan_add2<<<(unsigned)nb, SCAN_T, 0, st>>>(out, tmp, n); lc.end(st);
+    return;
+  }
   scan_rec(tmp, tmp, nb, tmp + nb, tmp_cap - nb, st, lc);
   lc.begin("k_scan_add", st); k_scan_add<<<(unsigned)nb, SCAN_T, 0, st>>>(out, tmp, n); lc.end(st);
 }
