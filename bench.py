@@ -383,6 +383,8 @@ def run_glio(args, rank, world, local_rank):
         pr = ctx.window_marginalize(r["poses"], r["speed_bias"], hfB)
         return len(r["steps"]), r, pr
 
+    step_wall = {}
+
     def timed_run(nsteps, sampler=None):
         iters = 0
         marks = {0, nsteps // 2, nsteps - 1}            # three NVML reads per run: a read stalls the launch queue for 0.5 - 4 ms depending on the box
@@ -393,6 +395,7 @@ def run_glio(args, rank, world, local_rank):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(st)
+        tick = [t0]
         for si in range(nsteps):
             with torch.cuda.stream(st):
                 flush.fill_(1)                      # L2 flush between steps (256 MB > 126 MB L2), inside the timed region
@@ -400,19 +403,27 @@ def run_glio(args, rank, world, local_rank):
             iters += it
             if sampler is not None and si in marks:
                 sampler.sample()
+            tick.append(time.perf_counter())        # every step ends synchronised (the marginalisation returns host data)
         e1.record(st)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ms = max(e0.elapsed_time(e1), 0.0)
         if dist is not None:
             dist.barrier()
+        per = np.diff(np.array(tick)) * 1e3
+        after = [per[i + 1] for i in sorted(marks) if sampler is not None and i + 1 < nsteps]
+        step_wall.clear()
+        step_wall.update(p50=round(float(np.median(per)), 4), mean=round(float(per.mean()), 4), max=round(float(per.max()), 4), argmax=int(per.argmax()), all=[round(float(v), 3) for v in per],
+                         mean_of_steps_after_an_nvml_read=round(float(np.mean(after)), 4) if after else None)
         return iters, ms, wall
 
     # NVML is initialised and queried during the warm-up steps: the first query of a process can stall the GPU work queue for
     # tens of milliseconds on some boxes (measured: a fixed ~85 ms once per process), which must not land in the timed region.
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ctx.window_set_scans(dscans[1:W + 1])
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3)):                # warm-up steps are the timed step verbatim (flush included: the first launch
+        with torch.cuda.stream(st):                    # of torch's fill kernel loads its module lazily, 5 - 20 ms once per process)
+            flush.fill_(1)
         one_step(dmap)
         if sampler is not None:
             sampler.sample()
@@ -422,6 +433,7 @@ def run_glio(args, rank, world, local_rank):
     l0 = ctx.launch_count
     iters, ms, wall = timed_run(args.steps, sampler)
     launches = ctx.launch_count - l0
+    step_wall_value = dict(step_wall)
     clocks = sampler.result() if sampler else None
     # (B) the same K steps again with every kernel launch bracketed by CUDA events on the launching stream: the
     #     per-kernel durations the roofline uses (its step time is reported next to the value for transparency)
@@ -592,7 +604,7 @@ def run_glio(args, rank, world, local_rank):
                             point_layout="pcl::PointXYZI, 32 B per point (stride 8 floats), map and scans, resident and host legs",
                             l2="256 MB flush between steps inside the timed region; per-step working set > 126 MB L2; "
                                "K2 re-reads the 64 MB residual table every iteration as the real solve does",
-                            host_wall_ms_per_step=1e3 * wall / args.steps, ms_per_step_with_kernel_events=ms_prof / args.steps, knn_deferred_queries_per_step=n_fallback / args.steps, wall_split=split,
+                            host_wall_ms_per_step=1e3 * wall / args.steps, step_wall_ms=step_wall_value, ms_per_step_with_kernel_events=ms_prof / args.steps, knn_deferred_queries_per_step=n_fallback / args.steps, wall_split=split,
                             solve_split_ms=dict(total=round(1e3 * s.total_seconds, 3), evaluation=round(1e3 * s.eval_seconds, 3), band_cholesky=round(1e3 * s.linear_solver_seconds, 3)), kernels=kern),
                 e2e=dict(value=e2e, unit="iterations/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=tmax_e / args.steps,
                          how="pinned host buffers in the PointXYZI layout through the C ABI; per step: the rebuilt local map (32 MB; upload started when the previous solve has returned, overlapping that window's marginalisation, remainder in line) + the newest keyframe's scan (3.2 MB, copy stream, overlapping this window's solve; the other 19 scans are resident as after glio_window_slide) + per-iteration pose/result traffic; final poses and the prior stay on the host side"),

@@ -83,10 +83,13 @@ bool cholesky_solve_avx2(BandMat& A, const double* b, double* x) {
       int u = 0;
       for (; u + 4 <= la; u += 4) {
         const __m256d v0 = _mm256_loadu_pd(c0 + u), v1 = _mm256_loadu_pd(c1 + u), v2 = _mm256_loadu_pd(c2 + u), v3 = _mm256_loadu_pd(c3 + u);
-        __m256d pa = _mm256_fmadd_pd(a1, v1, _mm256_mul_pd(a0, v0)), qa = _mm256_fmadd_pd(a3, v3, _mm256_mul_pd(a2, v2));
-        __m256d pb = _mm256_fmadd_pd(b1, v1, _mm256_mul_pd(b0, v0)), qb = _mm256_fmadd_pd(b3, v3, _mm256_mul_pd(b2, v2));
-        _mm256_storeu_pd(ra + u, _mm256_sub_pd(_mm256_loadu_pd(ra + u), _mm256_add_pd(pa, qa)));
-        _mm256_storeu_pd(rb + u, _mm256_sub_pd(_mm256_loadu_pd(rb + u), _mm256_add_pd(pb, qb)));
+        // four chained fnmadds per row vector (independent across vectors and rows: the out-of-order core overlaps them)
+        __m256d xa = _mm256_loadu_pd(ra + u), xb = _mm256_loadu_pd(rb + u);
+        xa = _mm256_fnmadd_pd(a0, v0, xa); xb = _mm256_fnmadd_pd(b0, v0, xb);
+        xa = _mm256_fnmadd_pd(a1, v1, xa); xb = _mm256_fnmadd_pd(b1, v1, xb);
+        xa = _mm256_fnmadd_pd(a2, v2, xa); xb = _mm256_fnmadd_pd(b2, v2, xb);
+        xa = _mm256_fnmadd_pd(a3, v3, xa); xb = _mm256_fnmadd_pd(b3, v3, xb);
+        _mm256_storeu_pd(ra + u, xa); _mm256_storeu_pd(rb + u, xb);
       }
       {  // ragged end: la - u in [0,3] elements of row a, lb - u in [1,4] of row b
         const __m256d v0 = _mm256_loadu_pd(c0 + u), v1 = _mm256_loadu_pd(c1 + u), v2 = _mm256_loadu_pd(c2 + u), v3 = _mm256_loadu_pd(c3 + u);
@@ -134,6 +137,31 @@ bool cholesky_solve_avx2(BandMat& A, const double* b, double* x) {
   }
   for (int i = 0; i < n; ++i) if (!std::isfinite(x[i])) return false;
   return true;
+}
+
+// y = A x for a symmetric matrix in lower-band storage: one pass over the stored rows; row i contributes the dot product
+// A(i, k0..i-1) . x to y[i] and the axpy x[i] * A(i, k0..i-1) to y[k0..i-1] from the same loads (4 lanes each).
+void symv_avx2(const BandMat& A, const double* x, double* y) {
+  const int n = A.n, hb = A.hb, w = hb + 1;
+  const double* a = A.a.data();
+  for (int i = 0; i < n; ++i) y[i] = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const int k0 = std::max(0, i - hb);
+    const double* ri = a + (size_t)i * w + hb - i;
+    const double xi = x[i];
+    const __m256d vx = _mm256_set1_pd(xi);
+    __m256d acc = _mm256_setzero_pd();
+    int k = k0;
+    for (; k + 4 <= i; k += 4) {
+      const __m256d r = _mm256_loadu_pd(ri + k);
+      acc = _mm256_fmadd_pd(r, _mm256_loadu_pd(x + k), acc);
+      _mm256_storeu_pd(y + k, _mm256_fmadd_pd(r, vx, _mm256_loadu_pd(y + k)));
+    }
+    double t[4]; _mm256_storeu_pd(t, acc);
+    double s = (t[0] + t[1]) + (t[2] + t[3]);
+    for (; k < i; ++k) { s += ri[k] * x[k]; y[k] += ri[k] * xi; }
+    y[i] += s + ri[i] * xi;
+  }
 }
 
 }  // namespace detail

@@ -1251,8 +1251,9 @@ void build_bin_items(glio_ctx* c, int K) {
   c->bin_dirty = false; c->bin_K = K;
 }
 
-// device evaluation of all active binary residuals -> c->h_bin_diag (K x 28), c->h_bin_off (P x 36), synchronised
-void eval_binary_blocks(glio_ctx* c, int K, const double* poses, bool want_jac, double huber) {
+// device evaluation of all active binary residuals -> c->h_bin_diag (K x 28), c->h_bin_off (P x 36): everything is queued
+// (kernels, the all-reduce of a sharded run, the copies to pinned host memory); eval_binary_wait makes the result visible
+void eval_binary_launch(glio_ctx* c, int K, const double* poses, bool want_jac, double huber) {
   build_bin_items(c, K);
   const int P = (int)c->pairs.size();
   memcpy(c->h_bin_poses.p, poses, (size_t)K * 7 * sizeof(double));
@@ -1268,7 +1269,11 @@ void eval_binary_blocks(glio_ctx* c, int K, const double* poses, bool want_jac, 
   }
   GLIO_CUDA_TRY(cudaMemcpyAsync(c->h_bin_diag.p, c->d_bin_diag.p, (size_t)K * GLIO_NACC * sizeof(double), cudaMemcpyDeviceToHost, c->st));
   if (want_jac && P > 0) GLIO_CUDA_TRY(cudaMemcpyAsync(c->h_bin_off.p, c->d_bin_off.p, (size_t)P * 36 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-  GLIO_CUDA_TRY(cudaStreamSynchronize(c->st));
+}
+void eval_binary_wait(glio_ctx* c) { GLIO_CUDA_TRY(cudaStreamSynchronize(c->st)); }
+void eval_binary_blocks(glio_ctx* c, int K, const double* poses, bool want_jac, double huber) {
+  eval_binary_launch(c, K, poses, want_jac, huber);
+  eval_binary_wait(c);
 }
 
 }  // namespace
@@ -1384,26 +1389,36 @@ int glio_batch_solve(glio_ctx* c, int K, double* poses, double* speed_bias, glio
         for (int i = 0; i < 7; ++i) pz[7 * k + i] = xa[(size_t)na * k + i];
         if (sb) for (int i = 0; i < 9; ++i) sz[9 * k + i] = xa[(size_t)na * k + 7 + i];
       }
-      eval_binary_blocks(c, K, pz.data(), want_jac, 0.0);
+      // the device evaluates the LiDAR pairs (and a sharded run sums them over the ranks) while the host evaluates its own
+      // factors into the freshly reset band; the device blocks are added when they have arrived
+      eval_binary_launch(c, K, pz.data(), want_jac, 0.0);
       double ct = 0;
+      int hrc = 0;
+      if (want_jac) { H->reset(n, hb); std::fill(g, g + n, 0.0); }
+      if (host_factors) hrc = host_factors(user, K, pz.data(), sb ? sz.data() : nullptr, want_jac ? 1 : 0, want_jac ? H->a.data() : nullptr, want_jac ? H->hb : 0, g, &ct);
+      eval_binary_wait(c);
+      if (hrc != 0) return false;
       for (int k = 0; k < K; ++k) ct += c->h_bin_diag.p[(size_t)k * GLIO_NACC + 27];
       if (want_jac) {
-        H->reset(n, hb);
-        std::fill(g, g + n, 0.0);
+        const int w = H->hb + 1;
+        double* a = H->a.data();
         for (int k = 0; k < K; ++k) {
           const double* ob = c->h_bin_diag.p + (size_t)k * GLIO_NACC;
           int idx = 0;
           for (int p = 0; p < 6; ++p) for (int q = p; q < 6; ++q) { H->at(nt * k + q, nt * k + p) += ob[idx]; ++idx; }
-          for (int p = 0; p < 6; ++p) g[nt * k + p] = ob[21 + p];
+          for (int p = 0; p < 6; ++p) g[nt * k + p] += ob[21 + p];
         }
         for (size_t pi = 0; pi < c->pairs.size(); ++pi) {
           const int kc = c->pairs[pi]->cur, ko = c->pairs[pi]->oth;
-          const double* ob = c->h_bin_off.p + pi * 36;
-          for (int p = 0; p < 6; ++p) for (int q = 0; q < 6; ++q) H->add_sym(nt * kc + p, nt * ko + q, ob[6 * p + q]);
+          const double* ob = c->h_bin_off.p + pi * 36;                 // d2 cost / d x_cur[p] d x_oth[q]
+          if (kc > ko) {                                               // rows of cur, six contiguous band entries each
+            for (int p = 0; p < 6; ++p) { double* row = a + (size_t)(nt * kc + p) * w + (nt * ko - (nt * kc + p) + H->hb); for (int q = 0; q < 6; ++q) row[q] += ob[6 * p + q]; }
+          } else if (kc < ko) {                                        // stored transposed: rows of oth
+            for (int q = 0; q < 6; ++q) { double* row = a + (size_t)(nt * ko + q) * w + (nt * kc - (nt * ko + q) + H->hb); for (int p = 0; p < 6; ++p) row[p] += ob[6 * p + q]; }
+          } else {
+            for (int p = 0; p < 6; ++p) for (int q = 0; q < 6; ++q) H->add_sym(nt * kc + p, nt * ko + q, ob[6 * p + q]);
+          }
         }
-      }
-      if (host_factors) {
-        if (host_factors(user, K, pz.data(), sb ? sz.data() : nullptr, want_jac ? 1 : 0, want_jac ? H->a.data() : nullptr, want_jac ? H->hb : 0, g, &ct) != 0) return false;
       }
       *cost = ct;
       return std::isfinite(ct);

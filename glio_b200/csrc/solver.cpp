@@ -122,6 +122,10 @@ inline double norm(const std::vector<double>& a) { return std::sqrt(dot(a, a)); 
 // y = A x for a symmetric matrix in lower-band storage
 inline void symv(const BandMat& A, const std::vector<double>& x, std::vector<double>& y) {
   const int n = A.n, hb = A.hb, w = hb + 1;
+#if defined(__x86_64__)
+  static const bool fast = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma") && std::getenv("GLIO_NO_AVX2") == nullptr;
+  if (fast && hb >= 4) { detail::symv_avx2(A, x.data(), y.data()); return; }
+#endif
   for (int i = 0; i < n; ++i) y[i] = 0.0;
   for (int i = 0; i < n; ++i) {
     const double* ri = A.a.data() + (size_t)i * w + hb - i;

@@ -112,6 +112,7 @@ bool cholesky_solve(BandMat& A, const double* b, double* x);
 bool cholesky_solve_scalar(BandMat& A, const double* b, double* x);   // portable path
 #if defined(__x86_64__)
 bool cholesky_solve_avx2(BandMat& A, const double* b, double* x);     // band_chol_avx2.cpp; call only when the CPU has AVX2 + FMA
+void symv_avx2(const BandMat& A, const double* x, double* y);          // band_chol_avx2.cpp; y = A x (differs from the scalar loop by rounding only)
 #endif
 
 // real roots of a polynomial of degree <= 4 (highest power first), for the subspace dogleg

@@ -80,5 +80,15 @@ if rank == 0:
                           solve_ms=float(t_solve.item()) / a.solves, iterations_per_s=iters / (t_solve.item() * 1e-3), host_wall_ms=1e3 * wall / a.solves,
                           allreduce_us_per_eval=ar_us, termination=s.message.decode(), cost=[s.initial_cost, s.final_cost], gen_s=round(t_gen, 1),
                           pose_err=[float(np.abs(B["poses_init"][:, :3] - T[:, :3]).max()), float(np.abs(r["poses"][:, :3] - T[:, :3]).max())])))
+# host share of one solve: kernel time (CUDA events per launch) vs the solver's own wall-clock timers
+ctx.lib_profile(True)
+t0 = time.perf_counter(); r = ctx.batch_solve(B["poses_init"], None, hf, opt); wall1 = time.perf_counter() - t0
+prof = ctx.lib_profile_read(); ctx.lib_profile(False)
+if rank == 0:
+    s = r["summary"]
+    print(json.dumps(dict(host_share=dict(python_wall_ms=1e3 * wall1, solver_total_ms=1e3 * s.total_seconds, eval_ms=1e3 * s.eval_seconds,
+                                          linear_solver_ms=1e3 * s.linear_solver_seconds, evaluations=s.num_evaluations, jacobian_evaluations=s.num_jacobian_evaluations,
+                                          linear_solves=s.num_linear_solves, kernels_ms={k: round(v[0], 3) for k, v in prof.items()},
+                                          kernel_launches={k: v[1] for k, v in prof.items()}))))
 if hook: hook.close()
 if world > 1: dist_.destroy_process_group()
