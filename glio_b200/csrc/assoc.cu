@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(128, 6) k_knn_box(SearchArgs a) {
       lx = cx - 1; hx = cx + 1; ly = cy - 1; hy = cy + 1; lz = cz - 1; hz = cz + 1;
       thread_rings(g, qx, qy, qz, cx, cy, cz, 1, 1, rmax, t, d4f, sbnd + threadIdx.x);
     }
-    box_grow(g, qx, qy, qz, gate_r, rmax, lx, hx, ly, hy, lz, hz, t, d4f);
+    box_grow(g, qx, qy, qz, gate_r, rmax, lx, hx, ly, hy, lz, hz, t, d4f, a.grow_mode ? sbnd + threadIdx.x : nullptr);
   }
   store_top5(a, p, t);
 }
@@ -457,7 +457,7 @@ void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const Assoc
   SearchArgs sa;
   sa.grid = grid; sa.Qt = Qt; sa.pm = w.pm; sa.order = w.order; sa.gate_sq = (float)gates.max_radius;
   sa.knn_idx = w.knn_idx; sa.knn_sqd = w.knn_sqd; sa.n_fallback = w.n_fallback; sa.store_all_sqd = w.idx5 != nullptr;
-  sa.tile_rings = w.tile_rings; sa.deferred = w.deferred; sa.n_deferred = w.n_deferred;
+  sa.tile_rings = w.tile_rings; sa.grow_mode = w.grow_mode; sa.deferred = w.deferred; sa.n_deferred = w.n_deferred;
   GLIO_CUDA_TRY(cudaMemsetAsync(w.n_deferred, 0, sizeof(unsigned int), st));
   const unsigned ns = (unsigned)((Qt + 32 * KNN_WARPS - 1) / (32 * KNN_WARPS));
   if (w.knn_mode == 6) {

@@ -93,6 +93,7 @@ struct glio_ctx {
   DevBuf<int32_t> w_knn_idx;
   DevBuf<uint32_t> w_deferred;
   int tile_rings = 64;         // tuning hook: env GLIO_TILE_RINGS (>= 32: the tile pass scans all rings itself)
+  int grow_mode = 1;           // growth slabs of the box search: 1 = batched row bounds + row culling, 0 = row after row (env GLIO_KNN_GROW)
   int knn_mode = 2;            // 2: per-thread box growth (default, fastest measured); 3: same from the own cell; 1: per-thread ring growth; 0: warp-cooperative tile pass (env GLIO_KNN_MODE)
   DevBuf<float> w_knn_sqd;
   DevBuf<unsigned long long> d_stats;
@@ -188,7 +189,7 @@ AssocWork make_work(glio_ctx* c, int64_t Qt, bool pair) {
   AssocWork w{};
   w.Qt = Qt; w.pm = c->w_pm.p; w.seg = c->w_seg.p; w.order = c->w_order.p; w.status = c->w_status.p;
   w.knn_idx = c->w_knn_idx.p; w.knn_sqd = c->w_knn_sqd.p; w.n_fallback = c->d_stats.p;
-  w.knn_mode = c->knn_mode; w.tile_rings = c->tile_rings; w.deferred = c->w_deferred.p; w.n_deferred = reinterpret_cast<unsigned int*>(c->d_stats.p + 2);
+  w.knn_mode = c->knn_mode; w.tile_rings = c->tile_rings; w.grow_mode = c->grow_mode; w.deferred = c->w_deferred.p; w.n_deferred = reinterpret_cast<unsigned int*>(c->d_stats.p + 2);
   w.nsd = pair ? nullptr : c->w_nsd.p; w.weight = c->w_weight.p; w.normal_cent = pair ? c->w_nc.p : nullptr;
   if (c->prm.keep_debug) { w.idx5 = c->w_idx5.p; w.sqd5 = c->w_sqd5.p; w.plane = c->w_plane.p; }
   return w;
@@ -393,6 +394,7 @@ int glio_create(int device, const glio_params* params, glio_ctx** out) {
     c->device = device;
     if (params) c->prm = *params; else glio_default_params(&c->prm);
     if (const char* e = getenv("GLIO_KNN_MODE")) { const int v = atoi(e); if (v >= 0 && v <= 6) c->knn_mode = v; }
+    if (const char* e = getenv("GLIO_KNN_GROW")) { const int v = atoi(e); if (v >= 0 && v <= 1) c->grow_mode = v; }
     if (const char* e = getenv("GLIO_TILE_RINGS")) { const int v = atoi(e); if (v >= 1 && v < 64) c->tile_rings = v; }
     if (const char* e = getenv("GLIO_PTS_PER_CELL")) { const float v = (float)atof(e); if (v > 0.1f && v < 1000.f) c->pts_per_cell = v; }
     c->map.build_pairs = c->knn_mode == 4;

@@ -116,6 +116,7 @@ struct AssocWork {
   float* knn_sqd;       // [5][Qt] squared distances, sorted order
   unsigned long long* n_fallback;  // statistics: queries deferred from the tile pass to the single-query pass
   int tile_rings;       // rings scanned by the tile pass before deferring (>= 32: never defer)
+  int grow_mode;        // box growth slabs: see SearchArgs::grow_mode
   int knn_mode;         // 0: warp-cooperative tile pass, 1: per-thread ring growth, 2: per-thread box growth from 3x3x3, 3: box growth from the own cell, 4: staged tile search + team pass (knn_tile.cu)
   uint32_t* deferred;   // [Qt] sorted positions of deferred queries
   unsigned int* n_deferred;

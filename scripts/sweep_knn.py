@@ -1,5 +1,5 @@
 """K1a tuning sweep at BASELINE cfg 2 sizes: per-kernel times (library launch-event profiler) for several
-(points-per-cell, GLIO_KNN_MODE) settings given as SWEEP="ppc:mode,...", each checked bit-for-bit against the first.
+(points-per-cell, GLIO_KNN_MODE[, GLIO_KNN_GROW]) settings given as SWEEP="ppc:mode[:grow],...", each checked bit-for-bit against the first.
 Not a bench value."""
 import sys, os, hashlib
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -11,8 +11,9 @@ P = synth.window_problem(W=W, Q=Q, M=M)
 dmap = torch.from_numpy(P["map_xyz"]).cuda(); dscans = [torch.from_numpy(s).cuda() for s in P["scans"]]
 cfgs = [c.split(":") for c in os.environ.get("SWEEP", "8:1,8:2,8:3,6:2,12:2").split(",")]
 ref = None
-for ppc, mode in cfgs:
-    os.environ["GLIO_PTS_PER_CELL"] = ppc; os.environ["GLIO_KNN_MODE"] = mode
+for cfg in cfgs:
+    ppc, mode = cfg[0], cfg[1]; grow = cfg[2] if len(cfg) > 2 else "1"
+    os.environ["GLIO_PTS_PER_CELL"] = ppc; os.environ["GLIO_KNN_MODE"] = mode; os.environ["GLIO_KNN_GROW"] = grow
     ctx = api.Context(0)
     ctx.set_map(dmap); ctx.window_set_scans(dscans)
     nm = ctx.window_associate(P["poses_init"])          # warm-up
@@ -33,5 +34,5 @@ for ppc, mode in cfgs:
     same = dig == ref[0] and np.array_equal(nm, ref[1])
     line = " ".join("%s=%.3f" % (k.replace("k_", ""), v[0] / v[1]) for k, v in prof.items() if k.startswith("k_knn") or k.startswith("k_plane") or k in ("k_transform_hist", "k_order_scatter"))
     knn = sum(v[0] / v[1] for k, v in prof.items() if k.startswith("k_knn"))
-    print("mode=%s ppc=%s knn_total=%.3f ms exact=%s deferred=%d | %s" % (mode, ppc, knn, same, nfb, line), flush=True)
+    print("mode=%s grow=%s ppc=%s knn_total=%.3f ms exact=%s deferred=%d | %s" % (mode, grow, ppc, knn, same, nfb, line), flush=True)
     ctx.close()
