@@ -354,7 +354,7 @@ struct FitArgs {
 };
 
 #ifndef GLIO_FIT_MINBLOCKS
-#define GLIO_FIT_MINBLOCKS 4
+#define GLIO_FIT_MINBLOCKS 5
 #endif
 template <bool PAIR>
 __global__ void __launch_bounds__(128, GLIO_FIT_MINBLOCKS) k_plane_fit(FitArgs a) {
@@ -371,24 +371,25 @@ __global__ void __launch_bounds__(128, GLIO_FIT_MINBLOCKS) k_plane_fit(FitArgs a
   double n[3] = {0, 0, 0}, d = 0;
   double nl[3] = {0, 0, 0}, cl[3] = {0, 0, 0};
   if (id[4] != 0x7fffffff && (double)d4 < a.gates.max_radius) {           // Estimator.cpp:3651 / :3751
-    double A[3][5];
+    // the five neighbours are gathered twice (for the fit, and again for the validity test: L1 hits) so that the 15 doubles are
+    // not live across the QR: ~30 registers less, one more resident block per SM
+    int pos[5];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const float4 m = __ldg(&a.pts_sorted[__ldg(&a.sorted_pos[id[j]])]);
-      A[0][j] = (double)m.x; A[1][j] = (double)m.y; A[2][j] = (double)m.z;
-    }
+    for (int j = 0; j < 5; ++j) pos[j] = __ldg(&a.sorted_pos[id[j]]);
     double Aw[3][5];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int j = 0; j < 5; ++j) Aw[c][j] = A[c][j];
+    for (int j = 0; j < 5; ++j) {
+      const float4 m = __ldg(&a.pts_sorted[pos[j]]);
+      Aw[0][j] = (double)m.x; Aw[1][j] = (double)m.y; Aw[2][j] = (double)m.z;
+    }
     double x[3];
     plane_solve5(Aw, x);                                                    // :3661
     plane_from_solution(x, n, d);                                           // :3662-3663
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {                                           // :3667-3674
-      const double v = dadd(dadd(dadd(dmul(n[0], A[0][j]), dmul(n[1], A[1][j])), dmul(n[2], A[2][j])), d);
+      const float4 m = __ldg(&a.pts_sorted[pos[j]]);
+      const double v = dadd(dadd(dadd(dmul(n[0], (double)m.x), dmul(n[1], (double)m.y)), dmul(n[2], (double)m.z)), d);
       if (fabs(v) > a.gates.dist_thres) ok = false;
     }
     if (ok) {

@@ -143,3 +143,41 @@ def test_empty_inputs_are_argument_errors(ctx):
         ctx.set_map(np.zeros((0, 3), np.float32))
     ctx.set_map(wall(rng, 100))                                              # the context is still usable afterwards
     assert ctx.assoc_scan_to_map(0, wall(rng, 10), IDENT_T, IDENT_Q) >= 0
+
+
+def test_window_with_an_unmatched_keyframe_solves_like_the_oracle(oracle):
+    """one keyframe of the window sees nothing of the map (zero LiDAR residuals: its block is empty on the device) and one sees
+    very little: the solve leans on the host factors there and still follows the oracle iterate by iterate"""
+    from glio_b200 import api, synth
+    W, Q = 4, 1500
+    P = synth.window_problem(W=W, Q=Q, M=40000, seed=77)
+    scans = [s.copy() for s in P["scans"]]
+    scans[2] = scans[2] + np.float32([0, 0, 60.0])          # far above everything
+    scans[1] = scans[1][:7]                                  # seven points only
+    ctx = api.Context(0)
+    try:
+        ctx.set_map(P["map_xyz"]); ctx.window_set_scans(scans)
+        nm = ctx.window_associate(P["poses_init"])
+        assert nm[2] == 0 and nm[1] <= 7 and nm[0] > 100
+        prob = oracle.WindowProblem(P["poses_init"], None, P["q_lb"], P["t_lb"], huber_delta=1.0)
+        for k in range(W):
+            m = ctx.get_matches(k, len(scans[k]))
+            prob.add_unary(np.full(m["n"], k, np.int32), m["cp"], m["nsd"], ctx.params.lidar_const * m["weight"].astype(np.float64))
+        hf = api.HostFactorSet(); T = P["poses_true"]
+        sw = np.concatenate([np.full(3, 20.0), np.full(3, 50.0), np.zeros(9)])
+        a = (0, T[0, :3], T[0, 3:], None, sw); prob.add_prior(*a); hf.add_prior(*a)
+        for i in range(W - 1):
+            dq = synth.quat_mul(synth.quat_conj(T[i, 3:]), T[i + 1, 3:]); dp = synth.quat_to_R(T[i, 3:]).T @ (T[i + 1, :3] - T[i, :3])
+            a = (i, i + 1, dp, dq, np.zeros(3), 0.1, sw * 0.5); prob.add_between(*a); hf.add_between(*a)
+        e = ctx.eval_unary(P["poses_init"])
+        assert np.all(e["H"][2] == 0) and np.all(e["g"][2] == 0) and e["cost"][2] == 0
+        ro = prob.solve(oracle.solver_options(), mode=0)
+        rg = ctx.window_solve(P["poses_init"], None, hf, api.default_solver_options())
+        assert rg["summary"].num_iterations == ro["summary"].num_iterations >= 2
+        assert len(rg["steps"]) == len(ro["steps"])
+        for a, b in zip(rg["steps"], ro["steps"]):
+            a = a.reshape(W, 6); b = b.reshape(W, 6)
+            assert np.max(np.abs(a[:, :3] - b[:, :3])) <= 1e-6 and np.max(2 * np.linalg.norm(a[:, 3:] - b[:, 3:], axis=1)) <= 1e-8
+        assert np.max(np.abs(rg["poses"] - ro["poses"])) <= 1e-6
+    finally:
+        ctx.close()
