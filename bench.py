@@ -337,7 +337,26 @@ def microbench_run(torch, dist, local_rank, rank, world, peak, steps=10):
 # ----------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU, pinned to the CPUs NVML reports as local to that GPU: the step is a chain of short launches and
+    host-side waits on pinned memory, and a rank that floats to the other socket pays a remote hop on every one of them."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_glio(args, rank, world, local_rank):
+    n_bound = bind_to_gpu_numa_node(local_rank)
     import torch
     from glio_b200 import api
     torch.cuda.set_device(local_rank)
@@ -498,8 +517,11 @@ def run_glio(args, rank, world, local_rank):
     _, rlast, plast = one_step(dmap)
 
     tmax, tmax_e, it_sum, it_sum_e = ms, ms_e, iters, iters_e
+    per_rank = [[ms / args.steps, ms_e / args.steps]]
     if dist is not None:
         t = torch.tensor([ms, ms_e], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); tmax, tmax_e = t.tolist()
+        mine = torch.tensor([ms / args.steps, ms_e / args.steps], device="cuda"); allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine); per_rank = [[round(float(v), 4) for v in a.tolist()] for a in allr]
         c = torch.tensor([iters, iters_e], device="cuda", dtype=torch.float64); dist.all_reduce(c); it_sum, it_sum_e = c.tolist()
     peaks = {}
     try:
@@ -516,6 +538,8 @@ def run_glio(args, rank, world, local_rank):
         try:
             batch = dict(strong_scaling_K400=batch_run(torch, dist, local_rank, rank, world, K=args.batch_k, Q=CFG["Q"], solves=2,
                                                        check_against_single=True))
+            if world == 1 and not args.no_cfg4:          # BASELINE configs[2]: K = 200 keyframes on one GPU
+                batch["cfg3_K200"] = batch_run(torch, dist, local_rank, rank, world, K=200, Q=CFG["Q"], solves=2)
             if world >= 8 and not args.no_cfg4:
                 batch["cfg4_K2000"] = batch_run(torch, dist, local_rank, rank, world, K=2000, Q=CFG["Q"], solves=1, max_iter=20)
         except AssertionError:
@@ -604,7 +628,7 @@ def run_glio(args, rank, world, local_rank):
                             point_layout="pcl::PointXYZI, 32 B per point (stride 8 floats), map and scans, resident and host legs",
                             l2="256 MB flush between steps inside the timed region; per-step working set > 126 MB L2; "
                                "K2 re-reads the 64 MB residual table every iteration as the real solve does",
-                            host_wall_ms_per_step=1e3 * wall / args.steps, step_wall_ms=step_wall_value, ms_per_step_with_kernel_events=ms_prof / args.steps, knn_deferred_queries_per_step=n_fallback / args.steps, wall_split=split,
+                            host_wall_ms_per_step=1e3 * wall / args.steps, step_wall_ms=step_wall_value, per_rank_ms_per_step_value_e2e=per_rank, cpus_bound_to_gpu_numa_node=n_bound, ms_per_step_with_kernel_events=ms_prof / args.steps, knn_deferred_queries_per_step=n_fallback / args.steps, wall_split=split,
                             solve_split_ms=dict(total=round(1e3 * s.total_seconds, 3), evaluation=round(1e3 * s.eval_seconds, 3), band_cholesky=round(1e3 * s.linear_solver_seconds, 3)), kernels=kern),
                 e2e=dict(value=e2e, unit="iterations/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=tmax_e / args.steps,
                          how="pinned host buffers in the PointXYZI layout through the C ABI; per step: the rebuilt local map (32 MB; upload started when the previous solve has returned, overlapping that window's marginalisation, remainder in line) + the newest keyframe's scan (3.2 MB, copy stream, overlapping this window's solve; the other 19 scans are resident as after glio_window_slide) + per-iteration pose/result traffic; final poses and the prior stay on the host side"),
@@ -623,7 +647,7 @@ def main():
     ap.add_argument("--impl", default="glio", choices=["glio", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch", action="store_true", help="skip the keyframe-sharded batch object")
-    ap.add_argument("--no-cfg4", action="store_true", help="skip the K=2000 batch run at 8 GPUs")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the BASELINE cfg 3 (K=200, 1 GPU) / cfg 4 (K=2000, 8 GPUs) batch runs")
     ap.add_argument("--no-microbench", action="store_true", help="skip the cfg 5 microbench object")
     ap.add_argument("--batch-k", type=int, default=400)
     ap.add_argument("--cpu-subsample", type=int, default=1, help="cpu_baseline leg: use every n-th scan point")
