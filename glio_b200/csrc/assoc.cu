@@ -45,16 +45,17 @@ __global__ void __launch_bounds__(256) k_transform_hist(GridDesc grid, const Seg
   atomicAdd(&cell_count[cell_of_clamped(grid, p[0], p[1], p[2])], 1);
 }
 
-// ---- pass 2: scatter query ids in cell order (locality: a warp's queries share grid cells) -----------
+// ---- pass 2: scatter the queries into cell order (locality: a warp's queries share grid cells) -------
 __global__ void __launch_bounds__(256) k_order_scatter(GridDesc grid, int64_t Qt, const float4* __restrict__ pm,
                                                        const int* __restrict__ cell_start, int* __restrict__ fill,
-                                                       uint32_t* __restrict__ order) {
+                                                       float4* __restrict__ pmq) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= Qt) return;
   const float4 p = pm[g];
   const int c = cell_of_clamped(grid, p.x, p.y, p.z);
   const int pos = cell_start[c] + atomicAdd(&fill[c], 1);
-  order[pos] = (uint32_t)g;
+  pmq[pos] = make_float4(p.x, p.y, p.z, __int_as_float((int)g));   // the query itself travels in cell order with its scan index:
+                                                                     // K1a and K1b read it coalesced, one scattered store per query
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(32 * KNN_WARPS) k_knn_search(SearchArgs a) {
   const GridDesc& G = a.grid;
   const float INF = __int_as_float(0x7f800000);
   float qx = 0.f, qy = 0.f, qz = 0.f;
-  if (active) { const float4 q4 = a.pm[a.order[p]]; qx = q4.x; qy = q4.y; qz = q4.z; }
+  if (active) { const float4 q4 = a.pmq[p]; qx = q4.x; qy = q4.y; qz = q4.z; }
   const int cx = cell_coord(qx, G.ox, G.inv_cell), cy = cell_coord(qy, G.oy, G.inv_cell), cz = cell_coord(qz, G.oz, G.inv_cell);
   Top5 t;
   top5_init(t);
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(128, 7) k_knn_thread(SearchArgs a) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.Qt) return;
   const GridDesc& g = a.grid;
-  const float4 q4 = a.pm[a.order[p]];
+  const float4 q4 = a.pmq[p];
   const float qx = q4.x, qy = q4.y, qz = q4.z;
   Top5 t; top5_init(t);
   const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(128, 6) k_knn_box(SearchArgs a) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.Qt) return;
   const GridDesc& g = a.grid;
-  const float4 q4 = a.pm[a.order[p]];
+  const float4 q4 = a.pmq[p];
   const float qx = q4.x, qy = q4.y, qz = q4.z;
   Top5 t; top5_init(t);
   const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(128) k_knn_deferred(SearchArgs a) {
   const int rmax = (int)ceilf((sqrtf(a.gate_sq) + 2e-3f) * G.inv_cell) + 1;
   for (unsigned int it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < nd; it += nwarps) {
     const int64_t p = a.deferred[it];
-    const float4 q4 = a.pm[a.order[p]];
+    const float4 q4 = a.pmq[p];
     const float qx = q4.x, qy = q4.y, qz = q4.z;
     const int cx = cell_coord(qx, G.ox, G.inv_cell), cy = cell_coord(qy, G.oy, G.inv_cell), cz = cell_coord(qz, G.oz, G.inv_cell);
     Top5 t; top5_init(t);
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(128) k_knn_deferred(SearchArgs a) {
 struct FitArgs {
   int64_t Qt;
   const float4* pm;
-  const uint32_t* order;
+  const float4* pmq;          // queries in cell-sorted order, .w = scan index
   const int32_t* knn_idx;
   const float* knn_sqd;
   AssocGates gates;
@@ -353,15 +354,18 @@ struct FitArgs {
   double* plane;
 };
 
+#ifndef GLIO_FIT_REGATHER
+#define GLIO_FIT_REGATHER 1
+#endif
 #ifndef GLIO_FIT_MINBLOCKS
-#define GLIO_FIT_MINBLOCKS 5
+#define GLIO_FIT_MINBLOCKS (GLIO_FIT_REGATHER ? 5 : 4)
 #endif
 template <bool PAIR>
 __global__ void __launch_bounds__(128, GLIO_FIT_MINBLOCKS) k_plane_fit(FitArgs a) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.Qt) return;
-  const int64_t g = a.order[p];
-  const float4 q4 = a.pm[g];
+  const float4 q4 = a.pmq[p];
+  const int64_t g = __float_as_int(q4.w);
   int id[5];
 #pragma unroll
   for (int j = 0; j < 5; ++j) id[j] = a.knn_idx[(int64_t)j * a.Qt + p];
@@ -371,8 +375,9 @@ __global__ void __launch_bounds__(128, GLIO_FIT_MINBLOCKS) k_plane_fit(FitArgs a
   double n[3] = {0, 0, 0}, d = 0;
   double nl[3] = {0, 0, 0}, cl[3] = {0, 0, 0};
   if (id[4] != 0x7fffffff && (double)d4 < a.gates.max_radius) {           // Estimator.cpp:3651 / :3751
-    // the five neighbours are gathered twice (for the fit, and again for the validity test: L1 hits) so that the 15 doubles are
-    // not live across the QR: ~30 registers less, one more resident block per SM
+#if GLIO_FIT_REGATHER
+    // the five neighbours are gathered twice (for the fit, and again for the validity test: L1/L2 hits) so that the 15 doubles
+    // are not live across the QR: ~30 registers less, one more resident block per SM
     int pos[5];
 #pragma unroll
     for (int j = 0; j < 5; ++j) pos[j] = __ldg(&a.sorted_pos[id[j]]);
@@ -392,6 +397,28 @@ __global__ void __launch_bounds__(128, GLIO_FIT_MINBLOCKS) k_plane_fit(FitArgs a
       const double v = dadd(dadd(dadd(dmul(n[0], (double)m.x), dmul(n[1], (double)m.y)), dmul(n[2], (double)m.z)), d);
       if (fabs(v) > a.gates.dist_thres) ok = false;
     }
+#else
+    double A[3][5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const float4 m = __ldg(&a.pts_sorted[__ldg(&a.sorted_pos[id[j]])]);
+      A[0][j] = (double)m.x; A[1][j] = (double)m.y; A[2][j] = (double)m.z;
+    }
+    double Aw[3][5];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) Aw[c][j] = A[c][j];
+    double x[3];
+    plane_solve5(Aw, x);                                                    // :3661
+    plane_from_solution(x, n, d);                                           // :3662-3663
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {                                           // :3667-3674
+      const double v = dadd(dadd(dadd(dmul(n[0], A[0][j]), dmul(n[1], A[1][j])), dmul(n[2], A[2][j])), d);
+      if (fabs(v) > a.gates.dist_thres) ok = false;
+    }
+#endif
     if (ok) {
       w = weight_of(n, d, q4.x, q4.y, q4.z);                                // :3678-3679
       st = ((double)w > a.gates.weight_min) ? GLIO_MATCH_VALID : GLIO_MATCH_FAIL_WEIGHT;  // :3681
@@ -454,9 +481,9 @@ void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const Assoc
   lc.begin("k_transform_hist", st); k_transform_hist<<<nb, 256, 0, st>>>(grid, d_segs, nseg, Qt, w.pm, w.seg, cell_count.p); lc.end(st);
   exclusive_scan_i32(cell_count.p, cell_pos.p, ncell + 1, scan_tmp, st, lc);
   GLIO_CUDA_TRY(cudaMemsetAsync(cell_count.p, 0, (size_t)(ncell + 1) * sizeof(int), st));
-  lc.begin("k_order_scatter", st); k_order_scatter<<<nb, 256, 0, st>>>(grid, Qt, w.pm, cell_pos.p, cell_count.p, w.order); lc.end(st);
+  lc.begin("k_order_scatter", st); k_order_scatter<<<nb, 256, 0, st>>>(grid, Qt, w.pm, cell_pos.p, cell_count.p, w.pmq); lc.end(st);
   SearchArgs sa;
-  sa.grid = grid; sa.Qt = Qt; sa.pm = w.pm; sa.order = w.order; sa.gate_sq = (float)gates.max_radius;
+  sa.grid = grid; sa.Qt = Qt; sa.pm = w.pm; sa.pmq = w.pmq; sa.gate_sq = (float)gates.max_radius;
   sa.knn_idx = w.knn_idx; sa.knn_sqd = w.knn_sqd; sa.n_fallback = w.n_fallback; sa.store_all_sqd = w.idx5 != nullptr;
   sa.tile_rings = w.tile_rings; sa.grow_mode = w.grow_mode; sa.deferred = w.deferred; sa.n_deferred = w.n_deferred;
   GLIO_CUDA_TRY(cudaMemsetAsync(w.n_deferred, 0, sizeof(unsigned int), st));
@@ -479,7 +506,7 @@ void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const Assoc
     if (w.tile_rings < 32) { lc.begin("k_knn_deferred", st); k_knn_deferred<<<148 * 8, 128, 0, st>>>(sa); lc.end(st); }
   }
   FitArgs fa;
-  fa.Qt = Qt; fa.pm = w.pm; fa.order = w.order; fa.knn_idx = w.knn_idx; fa.knn_sqd = w.knn_sqd; fa.gates = gates;
+  fa.Qt = Qt; fa.pm = w.pm; fa.pmq = w.pmq; fa.knn_idx = w.knn_idx; fa.knn_sqd = w.knn_sqd; fa.gates = gates;
   fa.pts_sorted = gb.pts.p; fa.sorted_pos = gb.sorted_pos.p; fa.oth_local = oth_local; fa.oth_stride = oth_stride;
   fa.status = w.status; fa.nsd = w.nsd; fa.weight = w.weight; fa.normal_cent = w.normal_cent;
   fa.idx5 = w.idx5; fa.sqd5 = w.sqd5; fa.plane = w.plane;

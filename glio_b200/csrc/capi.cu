@@ -82,9 +82,8 @@ struct glio_ctx {
   PinnedBuf<double> h_bin_diag, h_bin_off, h_bin_poses;
 
   // association workspace
-  DevBuf<float4> w_pm, w_nsd;
+  DevBuf<float4> w_pm, w_pmq, w_nsd;
   DevBuf<uint16_t> w_seg;
-  DevBuf<uint32_t> w_order;
   DevBuf<uint8_t> w_status;
   DevBuf<float> w_weight;
   DevBuf<double> w_nc, w_plane;
@@ -176,7 +175,7 @@ const float* stage_points(glio_ctx* c, DevBuf<float>& buf, const float* xyz, int
 }
 
 void ensure_work(glio_ctx* c, int64_t Qt, bool pair) {
-  c->w_pm.reserve((size_t)Qt); c->w_seg.reserve((size_t)Qt); c->w_order.reserve((size_t)Qt);
+  c->w_pm.reserve((size_t)Qt); c->w_pmq.reserve((size_t)Qt); c->w_seg.reserve((size_t)Qt);
   c->w_status.reserve((size_t)Qt); c->w_weight.reserve((size_t)Qt);
   c->w_flags.reserve((size_t)Qt + 1); c->w_pos.reserve((size_t)Qt + 1);
   c->w_knn_idx.reserve((size_t)Qt * 5); c->w_knn_sqd.reserve((size_t)Qt * 5); c->w_deferred.reserve((size_t)2 * Qt);
@@ -187,7 +186,7 @@ void ensure_work(glio_ctx* c, int64_t Qt, bool pair) {
 
 AssocWork make_work(glio_ctx* c, int64_t Qt, bool pair) {
   AssocWork w{};
-  w.Qt = Qt; w.pm = c->w_pm.p; w.seg = c->w_seg.p; w.order = c->w_order.p; w.status = c->w_status.p;
+  w.Qt = Qt; w.pm = c->w_pm.p; w.pmq = c->w_pmq.p; w.seg = c->w_seg.p; w.status = c->w_status.p;
   w.knn_idx = c->w_knn_idx.p; w.knn_sqd = c->w_knn_sqd.p; w.n_fallback = c->d_stats.p;
   w.knn_mode = c->knn_mode; w.tile_rings = c->tile_rings; w.grow_mode = c->grow_mode; w.deferred = c->w_deferred.p; w.n_deferred = reinterpret_cast<unsigned int*>(c->d_stats.p + 2);
   w.nsd = pair ? nullptr : c->w_nsd.p; w.weight = c->w_weight.p; w.normal_cent = pair ? c->w_nc.p : nullptr;
@@ -423,7 +422,7 @@ void glio_destroy(glio_ctx* c) {
   c->d_bin_items.release(); c->d_pair_item_start.release(); c->d_kf_inc_start.release(); c->d_inc.release(); c->d_bin_partials.release();
   c->d_pair_sums.release(); c->d_bin_diag.release(); c->d_bin_off.release(); c->d_bin_poses.release(); c->h_bin_diag.release(); c->h_bin_off.release(); c->h_bin_poses.release();
   for (auto& s : c->slots) if (s) s->release();
-  c->w_pm.release(); c->w_nsd.release(); c->w_seg.release(); c->w_order.release(); c->w_status.release(); c->w_weight.release();
+  c->w_pm.release(); c->w_pmq.release(); c->w_nsd.release(); c->w_seg.release(); c->w_status.release(); c->w_weight.release();
   c->w_nc.release(); c->w_plane.release(); c->w_idx5.release(); c->w_sqd5.release(); c->w_flags.release(); c->w_pos.release();
   c->cell_count.release(); c->cell_pos.release(); c->scan_tmp.release(); c->d_segs.release(); c->d_dst.release(); c->d_counts.release();
   c->h_counts.release(); c->d_bad.release(); c->d_keep.release(); c->d_items.release(); c->d_kf_item_start.release();

@@ -110,8 +110,8 @@ struct AssocGates {
 struct AssocWork {
   int64_t Qt;
   float4* pm;           // transformed query (x,y,z, _)
+  float4* pmq;          // the same, cell-sorted order, .w = bitcast scan index (written by k_order_scatter)
   uint16_t* seg;        // segment id of the query
-  uint32_t* order;      // queries sorted by grid cell
   int32_t* knn_idx;     // [5][Qt] neighbour indices, sorted order (K1a -> K1b)
   float* knn_sqd;       // [5][Qt] squared distances, sorted order
   unsigned long long* n_fallback;  // statistics: queries deferred from the tile pass to the single-query pass

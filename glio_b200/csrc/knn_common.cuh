@@ -52,8 +52,8 @@ __device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2
 struct SearchArgs {
   GridDesc grid;
   int64_t Qt;
-  const float4* pm;
-  const uint32_t* order;
+  const float4* pm;     // transformed queries, scan order
+  const float4* pmq;    // the same in cell-sorted order, .w = bitcast scan index (k_order_scatter)
   float gate_sq;
   int32_t* knn_idx;     // [5][Qt] sorted order
   float* knn_sqd;       // [5][Qt] sorted order; rows 0..3 are written only when store_all_sqd (the gate needs the 5th only)

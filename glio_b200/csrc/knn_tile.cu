@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(32 * TK_WARPS) k_knn_tile(TileArgs ta) {
   WarpTile wt = warp_tile_init(tk_smem, wid, lane);
 
   float qx = 0.f, qy = 0.f, qz = 0.f;
-  if (active) { const float4 q4 = a.pm[a.order[p]]; qx = q4.x; qy = q4.y; qz = q4.z; }
+  if (active) { const float4 q4 = a.pmq[p]; qx = q4.x; qy = q4.y; qz = q4.z; }
   const QueryRegs q = make_query(qx, qy, qz);
   const int cx = cell_coord(qx, G.ox, G.inv_cell), cy = cell_coord(qy, G.oy, G.inv_cell), cz = cell_coord(qz, G.oz, G.inv_cell);
   const float gate_r = sqrtf(a.gate_sq) + 2e-3f;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(32 * TK_WARPS) k_knn_tile2(TileArgs ta) {
     float qx = 0.f, qy = 0.f, qz = 0.f, T = 0.f;
     if (valid) {
       p = a.deferred[item];
-      const float4 q4 = a.pm[a.order[p]];
+      const float4 q4 = a.pmq[p];
       qx = q4.x; qy = q4.y; qz = q4.z;
       T = fminf(a.knn_sqd[4 * a.Qt + p], gate_cap);       // exact 5th distance inside the first pass's box (a proven bound), or the gate
     }
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(128, 12) k_knn_team(SearchArgs a, const uint32
     float qx = 0.f, qy = 0.f, qz = 0.f, T = 0.f;
     if (valid) {
       p = qlist[item];
-      const float4 q4 = a.pm[a.order[p]];
+      const float4 q4 = a.pmq[p];
       qx = q4.x; qy = q4.y; qz = q4.z;
       T = fminf(a.knn_sqd[4 * a.Qt + p], gate_cap);      // the first pass's 5th distance inside its box, or +inf
     }
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(128, 6) k_knn_box_start(TileArgs ta) {
   const GridDesc& g = a.grid;
   bool open = false;
   if (p < a.Qt) {
-    const float4 q4 = a.pm[a.order[p]];
+    const float4 q4 = a.pmq[p];
     const float qx = q4.x, qy = q4.y, qz = q4.z;
     Top5 t; top5_init(t);
     const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(128, 6) k_knn_grow(TileArgs ta) {
   const int rmax = (int)ceilf(gate_r * g.inv_cell) + 1;
   for (unsigned int item = blockIdx.x * blockDim.x + threadIdx.x; item < nd; item += gridDim.x * blockDim.x) {
     const int64_t p = a.deferred[item];
-    const float4 q4 = a.pm[a.order[p]];
+    const float4 q4 = a.pmq[p];
     const float qx = q4.x, qy = q4.y, qz = q4.z;
     const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
     Top5 t;
@@ -578,7 +578,7 @@ __global__ void __launch_bounds__(128, 6) k_knn_box_far(SearchArgs a) {
   const GridDesc& g = a.grid;
   bool far = false;
   if (p < a.Qt) {
-    const float4 q4 = a.pm[a.order[p]];
+    const float4 q4 = a.pmq[p];
     const float qx = q4.x, qy = q4.y, qz = q4.z;
     Top5 t; top5_init(t);
     const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(32 * FAR_WARPS) k_knn_far(SearchArgs a, const 
   unsigned long long* keys = s_keys[wid];
   for (unsigned int item = blockIdx.x * FAR_WARPS + wid; item < nd; item += nwarps) {
     const int64_t p = qlist[item];
-    const float4 q4 = a.pm[a.order[p]];
+    const float4 q4 = a.pmq[p];
     const float qx = q4.x, qy = q4.y, qz = q4.z;
     const float r = sqrtf(T0) * 1.001f + 2e-3f;
     const int ylo = max(cell_coord(qy - r, G.oy, G.inv_cell), 0), yhi = min(cell_coord(qy + r, G.oy, G.inv_cell), G.ny - 1);
