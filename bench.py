@@ -563,7 +563,7 @@ def run_glio(args, rank, world, local_rank):
     for name, (tot_ms, cnt) in prof.items():
         kern[name] = dict(ms_total=round(tot_ms, 4), launches=cnt, ms_avg=round(tot_ms / max(cnt, 1), 5))
     roof = None
-    knn_names = ("k_knn_search", "k_knn_deferred", "k_knn_thread", "k_knn_box", "k_knn_tile", "k_knn_tile2", "k_knn_team", "k_knn_box_start", "k_knn_grow", "k_knn_box_far", "k_knn_far")
+    knn_names = ("k_knn_search", "k_knn_deferred", "k_knn_thread", "k_knn_box", "k_knn_tile", "k_knn_tile2", "k_knn_team", "k_knn_box_start", "k_knn_grow", "k_knn_box_far", "k_knn_far", "k_knn_box_cells")
     if any(k in prof for k in knn_names) and "k_plane_fit" in prof:
         # K1 is one association pass issued as two launches (exact 5-NN search, then the fp64 plane fit)
         used = [k for k in knn_names + ("k_plane_fit",) if k in prof and prof[k][1]]

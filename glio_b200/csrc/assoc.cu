@@ -488,7 +488,9 @@ void assoc_run(const GridBuild& gb, const SegDesc* d_segs, int nseg, const Assoc
   sa.tile_rings = w.tile_rings; sa.grow_mode = w.grow_mode; sa.deferred = w.deferred; sa.n_deferred = w.n_deferred;
   GLIO_CUDA_TRY(cudaMemsetAsync(w.n_deferred, 0, sizeof(unsigned int), st));
   const unsigned ns = (unsigned)((Qt + 32 * KNN_WARPS - 1) / (32 * KNN_WARPS));
-  if (w.knn_mode == 6) {
+  if (w.knn_mode == 7) {
+    knn_box_cells_run(sa, st, lc);
+  } else if (w.knn_mode == 6) {
     knn_box_far_run(sa, st, lc);
   } else if (w.knn_mode == 5) {
     knn_box2_run(sa, cell_count, scan_tmp, st, lc);

@@ -93,7 +93,7 @@ struct glio_ctx {
   DevBuf<uint32_t> w_deferred;
   int tile_rings = 64;         // tuning hook: env GLIO_TILE_RINGS (>= 32: the tile pass scans all rings itself)
   int grow_mode = 1;           // growth slabs of the box search: 1 = batched row bounds + row culling, 0 = row after row (env GLIO_KNN_GROW)
-  int knn_mode = 2;            // 2: per-thread box growth (default, fastest measured); 3: same from the own cell; 1: per-thread ring growth; 0: warp-cooperative tile pass (env GLIO_KNN_MODE)
+  int knn_mode = 2;            // 2: per-thread box growth (default, fastest measured); 3: same from the own cell; 1: per-thread ring growth; 0: warp-cooperative tile pass; 4-7: the measured alternatives of knn_tile.cu (env GLIO_KNN_MODE)
   DevBuf<float> w_knn_sqd;
   DevBuf<unsigned long long> d_stats;
   DevBuf<int> w_flags, w_pos, cell_count, cell_pos, scan_tmp;
@@ -392,7 +392,7 @@ int glio_create(int device, const glio_params* params, glio_ctx** out) {
     c = new glio_ctx();
     c->device = device;
     if (params) c->prm = *params; else glio_default_params(&c->prm);
-    if (const char* e = getenv("GLIO_KNN_MODE")) { const int v = atoi(e); if (v >= 0 && v <= 6) c->knn_mode = v; }
+    if (const char* e = getenv("GLIO_KNN_MODE")) { const int v = atoi(e); if (v >= 0 && v <= 7) c->knn_mode = v; }
     if (const char* e = getenv("GLIO_KNN_GROW")) { const int v = atoi(e); if (v >= 0 && v <= 1) c->grow_mode = v; }
     if (const char* e = getenv("GLIO_TILE_RINGS")) { const int v = atoi(e); if (v >= 1 && v < 64) c->tile_rings = v; }
     if (const char* e = getenv("GLIO_PTS_PER_CELL")) { const float v = (float)atof(e); if (v > 0.1f && v < 1000.f) c->pts_per_cell = v; }

@@ -117,7 +117,7 @@ struct AssocWork {
   unsigned long long* n_fallback;  // statistics: queries deferred from the tile pass to the single-query pass
   int tile_rings;       // rings scanned by the tile pass before deferring (>= 32: never defer)
   int grow_mode;        // box growth slabs: see SearchArgs::grow_mode
-  int knn_mode;         // 0: warp-cooperative tile pass, 1: per-thread ring growth, 2: per-thread box growth from 3x3x3, 3: box growth from the own cell, 4: staged tile search + team pass (knn_tile.cu)
+  int knn_mode;         // 0: warp-cooperative tile pass, 1: per-thread ring growth, 2: per-thread box growth from 3x3x3, 3: box growth from the own cell, 4: staged tile search + team pass, 5: start box / growth in two launches, 6: far queries in a warp pass, 7: cell-by-cell start box (knn_tile.cu)
   uint32_t* deferred;   // [Qt] sorted positions of deferred queries
   unsigned int* n_deferred;
   uint8_t* status;

@@ -244,6 +244,7 @@ __device__ __forceinline__ void box_grow(const GridDesc& g, float qx, float qy, 
 void knn_tile_run(const SearchArgs& sa, const PairRec* d_pairs, DevBuf<int>& work, DevBuf<int>& scan_tmp, cudaStream_t st, LaunchCounter& lc);
 // K1a, box search split in two launches (GLIO_KNN_MODE=5): start box for everyone, face growth for the compacted rest
 void knn_box_far_run(const SearchArgs& sa, cudaStream_t st, LaunchCounter& lc);      // GLIO_KNN_MODE=6
+void knn_box_cells_run(const SearchArgs& sa, cudaStream_t st, LaunchCounter& lc);    // GLIO_KNN_MODE=7
 void knn_box2_run(const SearchArgs& sa, DevBuf<int>& work, DevBuf<int>& scan_tmp, cudaStream_t st, LaunchCounter& lc);
 
 }  // namespace glio

@@ -754,4 +754,78 @@ void knn_box_far_run(const SearchArgs& sa, cudaStream_t st, LaunchCounter& lc) {
   GLIO_CUDA_TRY(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// GLIO_KNN_MODE=7: the default box search with a CELL-BY-CELL start box.  At cfg-2 density the 5th neighbour sits 0.13 - 0.2 m
+// away while a cell is ~0.3 m wide, so a query's search sphere touches a handful of the 27 cells of its start box.  The four
+// cell boundaries of each of the nine rows are fetched up front (36 independent loads, parked in the thread's shared-memory
+// column); the own cell is scanned first, then the 6 face, 12 edge and 8 corner cells, each only if it can still hold something
+// nearer than the current 5th distance (per-axis gaps to the own cell's walls with the face-test margins, strict inequality: a
+// skipped cell holds only points strictly farther than the final 5th distance, so the box counts as scanned for the growth
+// proof).  Bit-exact - and 3.4x SLOWER than the nine-row start box (2.1 ms, profiles/r02_sweep_start_box.txt): a warp's
+// queries share a cell but not a pruning pattern, so the warp executes the union of the lanes' cells - all 27, with 27 loop
+// prologues instead of 9 - and the 27 inlined scan loops are 8 600 SASS instructions (137 KB, beyond the instruction cache).
+// Kept as the checkable form of that negative result.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float wall_gap2(float d) {
+  const float m = d * 0.999f - 2e-3f;
+  return m > 0.f ? m * m : 0.f;
+}
+#define GLIO_CELL(I, K, G2) \
+  if (!(d4f <= (G2))) scan_range_keys(g.pts, sb[((I) * 4 + (K)) * 128], sb[((I) * 4 + (K) + 1) * 128], qx, qy, qz, t, d4f);
+__device__ __forceinline__ void start_box_cells(const GridDesc& g, float qx, float qy, float qz, int cx, int cy, int cz, Top5& t, float& d4f, int* __restrict__ sb) {
+  const int* __restrict__ cs = g.cell_start;
+  const int xk0 = min(max(cx - 1, 0), g.nx), xk1 = min(max(cx, 0), g.nx), xk2 = min(max(cx + 1, 0), g.nx), xk3 = min(max(cx + 2, 0), g.nx);
+#pragma unroll
+  for (int dz = 0; dz < 3; ++dz) {
+    int b[12];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int z = cz + dz - 1, y = cy + dy - 1;
+      const bool ok = z >= 0 && z < g.nz && y >= 0 && y < g.ny;
+      const int row = (z * g.ny + y) * g.nx;
+      b[4 * dy + 0] = ok ? __ldg(&cs[row + xk0]) : 0; b[4 * dy + 1] = ok ? __ldg(&cs[row + xk1]) : 0;
+      b[4 * dy + 2] = ok ? __ldg(&cs[row + xk2]) : 0; b[4 * dy + 3] = ok ? __ldg(&cs[row + xk3]) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 12; ++j) sb[(dz * 12 + j) * 128] = b[j];
+  }
+  const float gxm = wall_gap2(qx - (g.ox + (float)cx * g.cell)), gxp = wall_gap2((g.ox + (float)(cx + 1) * g.cell) - qx);
+  const float gym = wall_gap2(qy - (g.oy + (float)cy * g.cell)), gyp = wall_gap2((g.oy + (float)(cy + 1) * g.cell) - qy);
+  const float gzm = wall_gap2(qz - (g.oz + (float)cz * g.cell)), gzp = wall_gap2((g.oz + (float)(cz + 1) * g.cell) - qz);
+  // row I = (dz+1)*3 + (dy+1), cell K = dx+1
+  GLIO_CELL(4, 1, -1.f)
+  GLIO_CELL(4, 0, gxm) GLIO_CELL(4, 2, gxp) GLIO_CELL(3, 1, gym) GLIO_CELL(5, 1, gyp) GLIO_CELL(1, 1, gzm) GLIO_CELL(7, 1, gzp)
+  GLIO_CELL(3, 0, gym + gxm) GLIO_CELL(3, 2, gym + gxp) GLIO_CELL(5, 0, gyp + gxm) GLIO_CELL(5, 2, gyp + gxp)
+  GLIO_CELL(1, 0, gzm + gxm) GLIO_CELL(1, 2, gzm + gxp) GLIO_CELL(7, 0, gzp + gxm) GLIO_CELL(7, 2, gzp + gxp)
+  GLIO_CELL(0, 1, gzm + gym) GLIO_CELL(2, 1, gzm + gyp) GLIO_CELL(6, 1, gzp + gym) GLIO_CELL(8, 1, gzp + gyp)
+  GLIO_CELL(0, 0, gzm + gym + gxm) GLIO_CELL(0, 2, gzm + gym + gxp) GLIO_CELL(2, 0, gzm + gyp + gxm) GLIO_CELL(2, 2, gzm + gyp + gxp)
+  GLIO_CELL(6, 0, gzp + gym + gxm) GLIO_CELL(6, 2, gzp + gym + gxp) GLIO_CELL(8, 0, gzp + gyp + gxm) GLIO_CELL(8, 2, gzp + gyp + gxp)
+}
+#undef GLIO_CELL
+
+__global__ void __launch_bounds__(128, 6) k_knn_box_cells(SearchArgs a) {
+  __shared__ int sbnd[36 * 128];
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.Qt) return;
+  const GridDesc& g = a.grid;
+  const float4 q4 = a.pmq[p];
+  const float qx = q4.x, qy = q4.y, qz = q4.z;
+  Top5 t; top5_init(t);
+  const int cx = cell_coord(qx, g.ox, g.inv_cell), cy = cell_coord(qy, g.oy, g.inv_cell), cz = cell_coord(qz, g.oz, g.inv_cell);
+  const float gate_r = sqrtf(a.gate_sq) + 2e-3f;
+  const int rmax = (int)ceilf(gate_r * g.inv_cell) + 1;
+  const bool far_out = cx < -rmax || cy < -rmax || cz < -rmax || cx >= g.nx + rmax || cy >= g.ny + rmax || cz >= g.nz + rmax;
+  float d4f = __int_as_float(0x7f800000);
+  if (!far_out) {
+    start_box_cells(g, qx, qy, qz, cx, cy, cz, t, d4f, sbnd + threadIdx.x);
+    box_grow(g, qx, qy, qz, gate_r, rmax, cx - 1, cx + 1, cy - 1, cy + 1, cz - 1, cz + 1, t, d4f, a.grow_mode ? sbnd + threadIdx.x : nullptr);
+  }
+  store_top5(a, p, t);
+}
+
+void knn_box_cells_run(const SearchArgs& sa, cudaStream_t st, LaunchCounter& lc) {
+  lc.begin("k_knn_box_cells", st); k_knn_box_cells<<<(unsigned)((sa.Qt + 127) / 128), 128, 0, st>>>(sa); lc.end(st);
+  GLIO_CUDA_TRY(cudaGetLastError());
+}
+
 }  // namespace glio

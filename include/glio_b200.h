@@ -80,7 +80,8 @@ int64_t glio_launch_count(const glio_ctx* ctx);
  * glio_profile_get sums the elapsed time of all launches of the named kernel since profiling was enabled
  * (names: K0 k_init_bounds, k_load_bounds, k_cell_hist, k_cell_scatter, k_make_pairs, k_scan_block, k_scan_add;
  * K1 k_transform_hist, k_order_scatter, k_knn_box [GLIO_KNN_MODE 2, default] | k_knn_thread [1] | k_knn_search + k_knn_deferred [0]
- * | k_knn_tile + k_defer_scatter + k_knn_tile2 + k_knn_team [4], k_plane_fit, k_plane_fit_pair, k_flags, k_compact;
+ * | k_knn_tile + k_defer_scatter + k_knn_tile2 + k_knn_team [4] | k_knn_box_start + k_knn_grow [5] | k_knn_box_far + k_knn_far [6]
+ * | k_knn_box_cells [7], k_plane_fit, k_plane_fit_pair, k_flags, k_compact;
  * K2 k_eval_unary, k_eval_unary_cost, k_eval_binary, k_eval_binary_cost, k_bin_assemble; local map k_lm_transform, k_vox_*;
  * front end k_feat_curvature, k_feat_select, k_feat_voxel, k_feat_offsets, k_feat_gather). */
 int glio_profile_enable(glio_ctx* ctx, int on);
