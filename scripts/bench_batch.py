@@ -16,6 +16,12 @@ ap.add_argument("--search-range", type=int, default=6); ap.add_argument("--sel",
 ap.add_argument("--solves", type=int, default=3); ap.add_argument("--max-iter", type=int, default=100)
 a = ap.parse_args()
 rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+n_bound = None
+if os.environ.get("GLIO_BIND", "1") != "0":             # host threads on the CPUs local to this rank's GPU (as bench.py does)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    n_bound = bench.bind_to_gpu_numa_node(local)
 torch.cuda.set_device(local)
 if world > 1:
     dist_.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -86,7 +92,7 @@ t0 = time.perf_counter(); r = ctx.batch_solve(B["poses_init"], None, hf, opt); w
 prof = ctx.lib_profile_read(); ctx.lib_profile(False)
 if rank == 0:
     s = r["summary"]
-    print(json.dumps(dict(host_share=dict(python_wall_ms=1e3 * wall1, solver_total_ms=1e3 * s.total_seconds, eval_ms=1e3 * s.eval_seconds,
+    print(json.dumps(dict(host_share=dict(cpus_bound=n_bound, python_wall_ms=1e3 * wall1, solver_total_ms=1e3 * s.total_seconds, eval_ms=1e3 * s.eval_seconds,
                                           linear_solver_ms=1e3 * s.linear_solver_seconds, evaluations=s.num_evaluations, jacobian_evaluations=s.num_jacobian_evaluations,
                                           linear_solves=s.num_linear_solves, kernels_ms={k: round(v[0], 3) for k, v in prof.items()},
                                           kernel_launches={k: v[1] for k, v in prof.items()}))))
