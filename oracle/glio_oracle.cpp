@@ -33,7 +33,8 @@ template <int N> Jet<N> operator*(const Jet<N>& f, const Jet<N>& g) { Jet<N> h; 
 template <int N> Jet<N> operator/(const Jet<N>& f, const Jet<N>& g) {
   // jet.h: h = f/g ; dh = (df - h dg)/g
   Jet<N> h; const double gi = 1.0 / g.a; const double fg = f.a * gi; h.a = fg;
-  for (int i = 0; i < N; ++i) h.v[i] = (f.v[i] - fg * g.v[i]) * gi; return h; }
+  for (int i = 0; i < N; ++i) h.v[i] = (f.v[i] - fg * g.v[i]) * gi;
+  return h; }
 template <int N> Jet<N> jsqrt(const Jet<N>& f) { Jet<N> h; const double t = std::sqrt(f.a); h.a = t; const double s = 1.0 / (2.0 * t); for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * s; return h; }
 inline double jsqrt(double x) { return std::sqrt(x); }
 template <int N> Jet<N>& operator+=(Jet<N>& f, const Jet<N>& g) { f = f + g; return f; }
@@ -765,7 +766,8 @@ void go_eval_edge(int mode, int W, const double* poses, const double q_lb[4], co
       JT qj[4] = {JT(q[0], 3), JT(q[1], 4), JT(q[2], 5), JT(q[3], 6)};
       JT res; edge_functor<JT>(cpd, ad, bd, q_lb, t_lb, s[i], tj, qj, &res);
       double jt[1][3], jq[1][4];
-      for (int cc = 0; cc < 3; ++cc) jt[0][cc] = res.v[cc]; for (int cc = 0; cc < 4; ++cc) jq[0][cc] = res.v[3 + cc];
+      for (int cc = 0; cc < 3; ++cc) jt[0][cc] = res.v[cc];
+      for (int cc = 0; cc < 4; ++cc) jq[0][cc] = res.v[3 + cc];
       const double* qs[1] = {q};
       finish_block(1, qs, res.a, jt, jq, 0, huber_delta, &r, J, &c);
     } else {

@@ -10,7 +10,7 @@
  * The oracle is authored from the reference *source* and from the published algorithms of its absent dependencies
  * (Eigen 3.3.4 ColPivHouseholderQR / Quaternion, FLANN 1.9 L2_Simple<float> KDTreeSingleIndex, PCL VoxelGrid, Ceres
  * 2.0.0 whose source IS vendored as a tarball).  PINNED (tests/test_oracle_pins.py, test_oracle_known_answers.py,
- * tests/cpp/*): the kNN bit for bit to OpenCV's bundled FLANN (KDTREE_SINGLE and LINEAR, also at M = 1 M), the 5x3 plane
+ * the C++ tests under tests/cpp): the kNN bit for bit to OpenCV's bundled FLANN (KDTREE_SINGLE and LINEAR, also at M = 1 M), the 5x3 plane
  * solve to LAPACK's pivoted QR, the Ceres pieces (corrector, loss, quaternion parameterization, dogleg, Levenberg-Marquardt,
  * Powell, polynomial roots) to Ceres' own known-answer tests.  PARITY UNPINNED for what no library in the image can check:
  * pcl::VoxelGrid, Eigen's packet-order reductions, std::sort's tie order (VoxelGrid, feature extraction).

@@ -363,7 +363,8 @@ void* go_problem_create(int W, const double* poses, const double* speed_bias, co
   P->W = W; P->has_sb = speed_bias != nullptr; P->nt = P->has_sb ? 15 : 6; P->na = P->has_sb ? 16 : 7; P->n = W * P->nt;
   P->x.assign((size_t)W * P->na, 0.0);
   for (int k = 0; k < W; ++k) { for (int i = 0; i < 7; ++i) P->x[(size_t)P->na * k + i] = poses[7 * k + i]; if (P->has_sb) for (int i = 0; i < 9; ++i) P->x[(size_t)P->na * k + 7 + i] = speed_bias[9 * k + i]; }
-  for (int i = 0; i < 4; ++i) P->q_lb[i] = q_lb[i]; for (int i = 0; i < 3; ++i) P->t_lb[i] = t_lb[i];
+  for (int i = 0; i < 4; ++i) P->q_lb[i] = q_lb[i];
+  for (int i = 0; i < 3; ++i) P->t_lb[i] = t_lb[i];
   P->huber = huber_delta;
   return P;
 }
@@ -378,8 +379,11 @@ void go_problem_add_binary(void* h, int64_t N, const int32_t* kf_c, const int32_
   P->bnc.insert(P->bnc.end(), nc, nc + 6 * N); P->bscore.insert(P->bscore.end(), score, score + N);
 }
 void go_problem_add_prior(void* h, int kf, const double t0[3], const double q0[4], const double* sb0, const double sw[15]) {
-  Prior f; f.kf = kf; for (int i = 0; i < 3; ++i) f.t0[i] = t0[i]; for (int i = 0; i < 4; ++i) f.q0[i] = q0[i];
-  for (int i = 0; i < 9; ++i) f.sb0[i] = sb0 ? sb0[i] : 0.0; for (int i = 0; i < 15; ++i) f.sw[i] = sw[i];
+  Prior f; f.kf = kf;
+  for (int i = 0; i < 3; ++i) f.t0[i] = t0[i];
+  for (int i = 0; i < 4; ++i) f.q0[i] = q0[i];
+  for (int i = 0; i < 9; ++i) f.sb0[i] = sb0 ? sb0[i] : 0.0;
+  for (int i = 0; i < 15; ++i) f.sw[i] = sw[i];
   ((Problem*)h)->priors.push_back(f);
 }
 void go_problem_add_between(void* h, int i, int j, const double dp[3], const double dq[4], const double dv[3], double dt, const double sw[15]) {
