@@ -395,12 +395,23 @@ def run_glio(args, rank, world, local_rank):
     hfB = factor_set(1, priorA)
     band = max(29, hfB.marg_half_bandwidth())
 
-    def one_step(m):
+    # The marginalisation's host half (Schur, decomposition, prior: ~0.15 ms) runs on the library's worker thread while the NEXT
+    # step's map and association are on the GPU (glio_window_marginalize_async); the job is joined right before the solve that
+    # would consume its prior, and the last one before the timed region ends: K steps contain K complete marginalisations.
+    pipelined = not args.sync_marg
+
+    class Done:                                      # a finished "job" for the synchronous variant
+        def __init__(self, prior): self.prior = prior
+        def wait(self): return self.prior
+
+    def one_step(m, pending=None):
         ctx.set_map(m)
         ctx.window_associate(posesB)
+        if pending is not None:
+            pending.wait()                           # the previous window's prior is complete before this solve starts
         r = ctx.window_solve(posesB, sb0, hfB, opts, band=band)
-        pr = ctx.window_marginalize(r["poses"], r["speed_bias"], hfB)
-        return len(r["steps"]), r, pr
+        job = ctx.window_marginalize_async(r["poses"], r["speed_bias"], hfB) if pipelined else Done(ctx.window_marginalize(r["poses"], r["speed_bias"], hfB))
+        return len(r["steps"]), r, job
 
     step_wall = {}
 
@@ -415,14 +426,16 @@ def run_glio(args, rank, world, local_rank):
         t0 = time.perf_counter()
         e0.record(st)
         tick = [t0]
+        job = None
         for si in range(nsteps):
             with torch.cuda.stream(st):
                 flush.fill_(1)                      # L2 flush between steps (256 MB > 126 MB L2), inside the timed region
-            it, _r, _p = one_step(dmap)
+            it, _r, job = one_step(dmap, job)
             iters += it
             if sampler is not None and si in marks:
                 sampler.sample()
-            tick.append(time.perf_counter())        # every step ends synchronised (the marginalisation returns host data)
+            tick.append(time.perf_counter())
+        job.wait()                                  # the last marginalisation completes inside the timed region
         e1.record(st)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -443,7 +456,7 @@ def run_glio(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):                # warm-up steps are the timed step verbatim (flush included: the first launch
         with torch.cuda.stream(st):                    # of torch's fill kernel loads its module lazily, 5 - 20 ms once per process)
             flush.fill_(1)
-        one_step(dmap)
+        one_step(dmap)[2].wait()
         if sampler is not None:
             sampler.sample()
     if sampler is not None:
@@ -480,16 +493,20 @@ def run_glio(args, rank, world, local_rank):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(st)
+        job = None
         for si in range(nsteps):
             with torch.cuda.stream(st):
                 flush.fill_(1)
             ctx.set_map(hmap)
             ctx.window_associate(posesB)
             ctx.window_set_scan(W - 1, hnew)        # next step's new keyframe: asynchronous, copy stream
+            if job is not None:
+                job.wait()
             r = ctx.window_solve(posesB, sb0, hfB, opts, band=band)
             ctx.map_prefetch(hmap)                  # the poses are final: the next window's rebuilt map starts its upload (copy stream)
-            ctx.window_marginalize(r["poses"], r["speed_bias"], hfB)
+            job = ctx.window_marginalize_async(r["poses"], r["speed_bias"], hfB) if pipelined else Done(ctx.window_marginalize(r["poses"], r["speed_bias"], hfB))
             iters += len(r["steps"])
+        job.wait()
         ctx.synchronize()                           # both streams: the last uploads are inside the timed region too
         e1.record(st)
         torch.cuda.synchronize()
@@ -514,7 +531,8 @@ def run_glio(args, rank, world, local_rank):
         ctx.window_marginalize(rs["poses"], rs["speed_bias"], hfB); t4 = time.perf_counter()
         split = dict(l2_flush_ms=round(1e3 * (t0 - tf), 3), set_map_ms=round(1e3 * (t1 - t0), 3), associate_ms=round(1e3 * (t2 - t1), 3),
                      solve_ms=round(1e3 * (t3 - t2), 3), marginalize_ms=round(1e3 * (t4 - t3), 3))
-    _, rlast, plast = one_step(dmap)
+    _, rlast, jlast = one_step(dmap)
+    plast = jlast.wait()
 
     tmax, tmax_e, it_sum, it_sum_e = ms, ms_e, iters, iters_e
     per_rank = [[ms / args.steps, ms_e / args.steps]]
@@ -628,7 +646,7 @@ def run_glio(args, rank, world, local_rank):
                             point_layout="pcl::PointXYZI, 32 B per point (stride 8 floats), map and scans, resident and host legs",
                             l2="256 MB flush between steps inside the timed region; per-step working set > 126 MB L2; "
                                "K2 re-reads the 64 MB residual table every iteration as the real solve does",
-                            host_wall_ms_per_step=1e3 * wall / args.steps, step_wall_ms=step_wall_value, per_rank_ms_per_step_value_e2e=per_rank, cpus_bound_to_gpu_numa_node=n_bound, ms_per_step_with_kernel_events=ms_prof / args.steps, knn_deferred_queries_per_step=n_fallback / args.steps, wall_split=split,
+                            host_wall_ms_per_step=1e3 * wall / args.steps, step_wall_ms=step_wall_value, per_rank_ms_per_step_value_e2e=per_rank, marginalisation=('pipelined: glio_window_marginalize_async, host half on the library worker thread under the next step\'s association, joined before the next solve; K steps contain K complete marginalisations' if pipelined else 'synchronous inside the step'), cpus_bound_to_gpu_numa_node=n_bound, ms_per_step_with_kernel_events=ms_prof / args.steps, knn_deferred_queries_per_step=n_fallback / args.steps, wall_split=split,
                             solve_split_ms=dict(total=round(1e3 * s.total_seconds, 3), evaluation=round(1e3 * s.eval_seconds, 3), band_cholesky=round(1e3 * s.linear_solver_seconds, 3)), kernels=kern),
                 e2e=dict(value=e2e, unit="iterations/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=tmax_e / args.steps,
                          how="pinned host buffers in the PointXYZI layout through the C ABI; per step: the rebuilt local map (32 MB; upload started when the previous solve has returned, overlapping that window's marginalisation, remainder in line) + the newest keyframe's scan (3.2 MB, copy stream, overlapping this window's solve; the other 19 scans are resident as after glio_window_slide) + per-iteration pose/result traffic; final poses and the prior stay on the host side"),
@@ -647,6 +665,7 @@ def main():
     ap.add_argument("--impl", default="glio", choices=["glio", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch", action="store_true", help="skip the keyframe-sharded batch object")
+    ap.add_argument("--sync-marg", action="store_true", help="run the marginalisation synchronously inside the step instead of pipelining its host half under the next association")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the BASELINE cfg 3 (K=200, 1 GPU) / cfg 4 (K=2000, 8 GPUs) batch runs")
     ap.add_argument("--no-microbench", action="store_true", help="skip the cfg 5 microbench object")
     ap.add_argument("--batch-k", type=int, default=400)

@@ -457,6 +457,37 @@ def _window_marginalize(self, poses, speed_bias, host_factors=None, eps=1e-8):
 Context.window_marginalize = _window_marginalize
 
 
+class MargJob:
+    """glio_marg_job: a marginalisation whose host half runs on the context's worker thread; wait() joins it -> MargPrior."""
+
+    def __init__(self, ctx, handle, keep):
+        self._ctx = ctx; self._h = handle; self._keep = keep          # keep: the arrays / factor set the job may still read
+
+    def wait(self):
+        assert self._h is not None, "job already waited for"
+        out = C.c_void_p()
+        h, self._h = self._h, None
+        self._ctx._chk(self._ctx._lib.glio_marg_job_wait(h, C.byref(out)))
+        self._keep = None
+        return MargPrior(out, self._ctx._lib)
+
+
+def _window_marginalize_async(self, poses, speed_bias, host_factors=None, eps=1e-8):
+    """glio_window_marginalize_async: queues the device half, runs the host callback, returns a MargJob at once."""
+    pb = np.ascontiguousarray(poses, np.float64).reshape(-1, 7); W = len(pb)
+    sb = np.ascontiguousarray(speed_bias, np.float64).reshape(W, 9)
+    if host_factors is None:
+        fn, user = C.cast(None, HOST_MARG_FN), None
+    else:
+        fn, user = C.cast(self._lib.glio_hf_marg_evaluate, HOST_MARG_FN), host_factors._h
+    job = C.c_void_p()
+    self._chk(self._lib.glio_window_marginalize_async(self._h, C.c_int(W), _ptr(pb), _ptr(sb), fn, user, C.c_double(eps), C.byref(job)))
+    return MargJob(self, job, (pb, sb, host_factors))
+
+
+Context.window_marginalize_async = _window_marginalize_async
+
+
 def _window_solve(self, poses, speed_bias=None, host_factors=None, options=None, max_log=64, band=None):
     """ceres::Solve for the window problem (Estimator.cpp:2424-2433).  Returns dict(poses, speed_bias, summary, iterations, steps)."""
     pb = np.array(poses, np.float64).reshape(-1, 7).copy(); W = len(pb)

@@ -2,6 +2,9 @@
 // No CPU fallback: without a CUDA device glio_create fails.
 #include <array>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <chrono>
 #include <deque>
 #include <map>
@@ -43,8 +46,32 @@ struct Slot {
 
 }  // namespace
 
+// One marginalisation whose host half (A/b assembly, Schur, eigen-decomposition, prior) runs on the context's worker thread while
+// the caller goes on (typically: hands the next window's association to the GPU).  The device half was queued by the caller.
+struct glio_marg_job {
+  glio_ctx* ctx = nullptr;
+  int W = 0;
+  double eps = 1e-8;
+  unsigned int epoch = 0;
+  std::vector<double> A, b;            // host-side accumulations (IMU / previous prior), marginalisation ordering
+  std::vector<double> x0_pose, x0_sb;  // linearisation point of the kept states
+  std::vector<double> out;             // snapshot of the device result (W x 28)
+  std::atomic<int> copied{0};          // the worker no longer needs the context's result buffer
+  std::atomic<int> done{0};
+  int rc = 0;
+  std::string err;
+  glio_marg_prior* prior = nullptr;
+};
+
 struct glio_ctx {
   int device = 0;
+  // worker thread of glio_window_marginalize_async (started lazily, joined by glio_destroy)
+  std::thread marg_thread;
+  std::mutex marg_mu;
+  std::condition_variable marg_cv;
+  glio_marg_job* marg_queued = nullptr;      // handed to the worker (guarded by marg_mu)
+  bool marg_quit = false;
+  glio_marg_job* marg_pending = nullptr;     // the job in flight, caller-thread view (one at a time)
   cudaStream_t st = nullptr;
   glio_params prm{};
   std::string err;
@@ -324,6 +351,13 @@ void fill_summary(const SolverSummary& S, int n, glio_solver_summary* summary, g
 // device evaluation of all active unary residuals -> c->h_out (W x 28: 21 upper-tri H, 6 g, 1 cost), synchronised
 // launch half: returns the epoch to wait for (0: nothing was launched, h_out already holds zeros)
 unsigned int eval_unary_launch(glio_ctx* c, int W, const double* poses_body, int jac_kind, bool want_jac) {
+  if (c->marg_pending) {            // an asynchronous marginalisation still owns the result buffer until its worker has copied it
+    while (!c->marg_pending->copied.load(std::memory_order_acquire)) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
   build_items(c, W);
   // Zero-copy round trip: the W poses travel in the kernel parameters, the last block writes the W x 28 result into
   // pinned host memory and raises an epoch flag the host spins on.  This replaces H2D copy + launch + D2H copy +
@@ -411,6 +445,12 @@ int glio_create(int device, const glio_params* params, glio_ctx** out) {
 void glio_destroy(glio_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->marg_thread.joinable()) {
+    if (c->marg_pending) { glio_marg_prior* dropped = nullptr; glio_marg_job_wait(c->marg_pending, &dropped); if (dropped) glio_marg_prior_destroy(dropped); }
+    { std::lock_guard<std::mutex> lk(c->marg_mu); c->marg_quit = true; }
+    c->marg_cv.notify_one();
+    c->marg_thread.join();
+  }
   if (c->st_copy) cudaStreamSynchronize(c->st_copy);
   if (c->st) cudaStreamSynchronize(c->st);
   c->map.release(); c->map_stage.release(); c->map_stage2.release(); if (c->ev_map) cudaEventDestroy(c->ev_map);
@@ -829,32 +869,118 @@ int glio_eval_unary(glio_ctx* c, int W, const double* poses_body, int jac_kind, 
 }
 
 // ---- K3: marginalisation of KF0 (MarginalizationInfo::PreMarginalize + Marginalize, MarginalizationFactor.cpp:107-202)
+}  // extern "C"
+
+namespace {
+
+// host half: the device blocks (W x 28 doubles: 21 upper-triangular H, 6 g, cost) join A/b, then Schur + decomposition + prior
+glio_marg_prior* marg_finish_host(int W, double eps, std::vector<double>& A, std::vector<double>& b, const double* hout,
+                                  const double* x0_pose, const double* x0_sb) {
+  const int N = 6 * W + 18, m = 15, n = N - m;
+  static const int ut[6][6] = {{0, 1, 2, 3, 4, 5}, {1, 6, 7, 8, 9, 10}, {2, 7, 11, 12, 13, 14}, {3, 8, 12, 15, 16, 17}, {4, 9, 13, 16, 18, 19}, {5, 10, 14, 17, 19, 20}};
+  for (int k = 0; k < W; ++k) {
+    const double* o = hout + (size_t)k * GLIO_NACC;
+    const int base = marg_index_t(k);                       // t at base, q at base + 3 in every keyframe of this ordering
+    for (int p = 0; p < 6; ++p) { b[base + p] += o[21 + p]; for (int q = 0; q < 6; ++q) A[(size_t)(base + p) * N + base + q] += o[ut[p][q]]; }
+  }
+  std::vector<double> LJ((size_t)n * n), lr(n);
+  if (marginalize_dense(A.data(), b.data(), N, m, eps, LJ.data(), lr.data()) != GLIO_OK) return nullptr;
+  return glio_marg_prior_create(W, LJ.data(), lr.data(), x0_pose, x0_sb);
+}
+
+// device half + the caller's host factors: queues the LiDAR re-evaluation of every keyframe with the ambient x,y,z quaternion
+// columns (Estimator.cpp:2538-2576) and evaluates the host callback while the kernel runs
+unsigned int marg_begin(glio_ctx* c, int W, const double* poses, const double* speed_bias, glio_host_marg_fn host_marg, void* user,
+                        std::vector<double>& A, std::vector<double>& b) {
+  const int N = 6 * W + 18;
+  const unsigned int epoch = eval_unary_launch(c, W, poses, 1, true);
+  A.assign((size_t)N * N, 0.0); b.assign(N, 0.0);
+  if (host_marg) GLIO_REQUIRE(host_marg(user, W, poses, speed_bias, A.data(), b.data()) == 0, GLIO_ERR_STATE, "host_marg callback failed");
+  return epoch;
+}
+
+void marg_worker(glio_ctx* c) {
+  cudaSetDevice(c->device);
+  for (;;) {
+    glio_marg_job* j = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(c->marg_mu);
+      c->marg_cv.wait(lk, [&] { return c->marg_queued != nullptr || c->marg_quit; });
+      if (c->marg_quit && !c->marg_queued) return;
+      j = c->marg_queued; c->marg_queued = nullptr;
+    }
+    try {
+      eval_unary_wait(c, j->epoch);
+      j->out.assign(c->h_out.p, c->h_out.p + (size_t)j->W * GLIO_NACC);
+      j->copied.store(1, std::memory_order_release);
+      j->prior = marg_finish_host(j->W, j->eps, j->A, j->b, j->out.data(), j->x0_pose.data(), j->x0_sb.data());
+      if (!j->prior) { j->rc = GLIO_ERR_STATE; j->err = "marginalisation failed (decomposition or prior)"; }
+    } catch (const Error& e) { j->rc = e.code; j->err = e.msg; }
+    catch (const std::exception& e) { j->rc = GLIO_ERR_STATE; j->err = e.what(); }
+    j->copied.store(1, std::memory_order_release);
+    j->done.store(1, std::memory_order_release);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
 int glio_window_marginalize(glio_ctx* c, int W, const double* poses, const double* speed_bias, glio_host_marg_fn host_marg, void* user,
                             double eps, glio_marg_prior** prior_out) {
   if (!c || !prior_out) return GLIO_ERR_ARG;
   *prior_out = nullptr;
   return guarded(c, [&] {
     GLIO_REQUIRE(W >= 2 && W <= 4096 && poses && speed_bias, GLIO_ERR_ARG, "glio_window_marginalize: need W >= 2, poses and speed_bias");
-    const int N = 6 * W + 18, m = 15, n = N - m;
-    // LiDAR factors of every keyframe of the window with the ambient x,y,z quaternion columns (Estimator.cpp:2538-2576):
-    // device pass -> W x (21 upper-triangular H, 6 g, cost) in pinned host memory
-    const unsigned int epoch = eval_unary_launch(c, W, poses, 1, true);
-    std::vector<double> A((size_t)N * N, 0.0), b(N, 0.0);
-    // the host factors are evaluated while the kernel runs
-    if (host_marg) GLIO_REQUIRE(host_marg(user, W, poses, speed_bias, A.data(), b.data()) == 0, GLIO_ERR_STATE, "host_marg callback failed");
+    std::vector<double> A, b;
+    const unsigned int epoch = marg_begin(c, W, poses, speed_bias, host_marg, user, A, b);
     eval_unary_wait(c, epoch);
-    static const int ut[6][6] = {{0, 1, 2, 3, 4, 5}, {1, 6, 7, 8, 9, 10}, {2, 7, 11, 12, 13, 14}, {3, 8, 12, 15, 16, 17}, {4, 9, 13, 16, 18, 19}, {5, 10, 14, 17, 19, 20}};
-    for (int k = 0; k < W; ++k) {
-      const double* o = c->h_out.p + (size_t)k * GLIO_NACC;
-      const int base = marg_index_t(k);                       // t at base, q at base + 3 in every keyframe of this ordering
-      for (int p = 0; p < 6; ++p) { b[base + p] += o[21 + p]; for (int q = 0; q < 6; ++q) A[(size_t)(base + p) * N + base + q] += o[ut[p][q]]; }
-    }
-    std::vector<double> LJ((size_t)n * n), lr(n);
-    GLIO_REQUIRE(marginalize_dense(A.data(), b.data(), N, m, eps, LJ.data(), lr.data()) == GLIO_OK, GLIO_ERR_STATE, "marginalize_dense failed");
-    glio_marg_prior* made = glio_marg_prior_create(W, LJ.data(), lr.data(), poses + 7, speed_bias + 9);
-    GLIO_REQUIRE(made != nullptr, GLIO_ERR_STATE, "glio_marg_prior_create failed");
+    glio_marg_prior* made = marg_finish_host(W, eps, A, b, c->h_out.p, poses + 7, speed_bias + 9);
+    GLIO_REQUIRE(made != nullptr, GLIO_ERR_STATE, "marginalisation failed (decomposition or prior)");
     *prior_out = made;
   });
+}
+
+// The same pass with its host half on the context's worker thread: returns as soon as the device half is queued and the host
+// callback has run; the Schur complement, the decomposition and the prior are computed while the caller hands the next window's
+// association to the GPU.  One job at a time per context; glio_marg_job_wait joins it (and must be called before the next solve
+// needs the prior).  Results are identical to glio_window_marginalize.
+int glio_window_marginalize_async(glio_ctx* c, int W, const double* poses, const double* speed_bias, glio_host_marg_fn host_marg, void* user,
+                                  double eps, glio_marg_job** job_out) {
+  if (!c || !job_out) return GLIO_ERR_ARG;
+  *job_out = nullptr;
+  return guarded(c, [&] {
+    GLIO_REQUIRE(W >= 2 && W <= 4096 && poses && speed_bias, GLIO_ERR_ARG, "glio_window_marginalize_async: need W >= 2, poses and speed_bias");
+    GLIO_REQUIRE(c->marg_pending == nullptr, GLIO_ERR_STATE, "glio_window_marginalize_async: the previous job has not been waited for");
+    std::unique_ptr<glio_marg_job> j(new glio_marg_job());
+    j->ctx = c; j->W = W; j->eps = eps;
+    j->x0_pose.assign(poses + 7, poses + 7 * (size_t)W); j->x0_sb.assign(speed_bias + 9, speed_bias + 18);
+    j->epoch = marg_begin(c, W, poses, speed_bias, host_marg, user, j->A, j->b);
+    if (!c->marg_thread.joinable()) c->marg_thread = std::thread(marg_worker, c);
+    { std::lock_guard<std::mutex> lk(c->marg_mu); c->marg_queued = j.get(); }
+    c->marg_cv.notify_one();
+    c->marg_pending = j.get();
+    *job_out = j.release();
+  });
+}
+
+int glio_marg_job_wait(glio_marg_job* j, glio_marg_prior** prior_out) {
+  if (!j) return GLIO_ERR_ARG;
+  if (prior_out) *prior_out = nullptr;
+  for (unsigned long long spins = 0; !j->done.load(std::memory_order_acquire); ++spins) {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((spins & 0xfffull) == 0xfffull) std::this_thread::yield();
+  }
+  glio_ctx* c = j->ctx;
+  if (c && c->marg_pending == j) c->marg_pending = nullptr;
+  const int rc = j->rc;
+  if (rc != GLIO_OK) { if (c) c->err = j->err; if (j->prior) glio_marg_prior_destroy(j->prior); }
+  else if (prior_out) *prior_out = j->prior;
+  else if (j->prior) glio_marg_prior_destroy(j->prior);
+  delete j;
+  return rc;
 }
 
 // ---- front-end feature extraction: Preprocessing::cloudHandler, GLIO/src/Preprocessing.cpp:529-655

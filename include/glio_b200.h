@@ -286,6 +286,15 @@ typedef int (*glio_host_marg_fn)(void* user, int W, const double* poses, const d
 typedef struct glio_marg_prior glio_marg_prior;
 int glio_window_marginalize(glio_ctx* ctx, int W, const double* poses, const double* speed_bias, glio_host_marg_fn host_marg, void* user,
                             double eps /* 1e-8 in the reference */, glio_marg_prior** prior_out);
+/* The same pass with its host half (A/b assembly, Schur complement, decomposition, prior: ~0.15 ms) on a worker thread of the
+ * context: the call returns when the device half is queued and host_marg has run, so the caller can hand the NEXT window's map and
+ * association to the GPU meanwhile (the reference does these strictly one after the other, Estimator.cpp:2462-2608 then the next
+ * processImage).  One job at a time per context.  glio_marg_job_wait joins the job, frees it and returns the prior (identical to
+ * glio_window_marginalize's); call it before the next solve needs the prior.  glio_destroy joins an abandoned job. */
+typedef struct glio_marg_job glio_marg_job;
+int glio_window_marginalize_async(glio_ctx* ctx, int W, const double* poses, const double* speed_bias, glio_host_marg_fn host_marg,
+                                  void* user, double eps, glio_marg_job** job_out);
+int glio_marg_job_wait(glio_marg_job* job, glio_marg_prior** prior_out);
 glio_marg_prior* glio_marg_prior_create(int W, const double* lin_jac, const double* lin_res, const double* x0_poses, const double* x0_sb);
 void glio_marg_prior_destroy(glio_marg_prior* p);
 int glio_marg_prior_size(const glio_marg_prior* p, int* n, int* W);

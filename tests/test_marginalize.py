@@ -204,3 +204,42 @@ def test_integrated_marginalisation_two_windows(oracle):
             oprior = dict(W=W, lin_jac=om["lin_jac"], lin_res=om["lin_res"], x0_pose=om["x0_pose"], x0_sb=om["x0_sb"])
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_async_marginalisation_equals_the_synchronous_pass(oracle):
+    """glio_window_marginalize_async: the host half runs on the context's worker thread while the caller re-associates (and even
+    evaluates) on the same context; the prior is bit-identical to the synchronous pass, twice in a row, and an abandoned job is
+    joined by glio_destroy"""
+    from glio_b200 import api, synth
+    W, Q = 5, 3000
+    P = synth.window_problem(W=W, Q=Q, M=60000, seed=41)
+    ctx = api.Context(0)
+    try:
+        ctx.set_map(P["map_xyz"]); ctx.window_set_scans(P["scans"])
+        ctx.window_associate(P["poses_init"])
+        rng = np.random.default_rng(3); sb = rng.normal(0, 0.05, (W, 9))
+        hf = api.HostFactorSet(); T = P["poses_true"]
+        sw = np.concatenate([np.full(3, 20.0), np.full(3, 50.0), np.full(9, 5.0)])
+        hf.add_prior(0, T[0, :3], T[0, 3:], sb[0], sw)
+        for i in range(W - 1):
+            dq = synth.quat_mul(synth.quat_conj(T[i, 3:]), T[i + 1, 3:]); dp = synth.quat_to_R(T[i, 3:]).T @ (T[i + 1, :3] - T[i, :3])
+            hf.add_between(i, i + 1, dp, dq, np.zeros(3), 0.1, sw * 0.5)
+        ref = ctx.window_marginalize(P["poses_init"], sb, hf).arrays()
+        for _ in range(2):
+            job = ctx.window_marginalize_async(P["poses_init"], sb, hf)
+            nm = ctx.window_associate(P["poses_init"])               # the GPU is busy with the next association meanwhile
+            e = ctx.eval_unary(P["poses_init"])                      # and a new evaluation must not disturb the job's result
+            got = job.wait().arrays()
+            for k in ("lin_jac", "lin_res", "A_info", "b_info", "x0_pose", "x0_sb"):
+                assert np.array_equal(got[k], ref[k]), k
+            assert nm.sum() > 0 and np.isfinite(e["cost"]).all()
+        with pytest.raises(api.GlioError):
+            j1 = ctx.window_marginalize_async(P["poses_init"], sb, hf)
+            try:
+                ctx.window_marginalize_async(P["poses_init"], sb, hf)     # one job at a time
+            finally:
+                j1.wait()
+        ctx.window_marginalize_async(P["poses_init"], sb, hf)        # abandoned: close() joins it
+    finally:
+        ctx.close()
