@@ -5,6 +5,10 @@
 #include <condition_variable>
 #include <mutex>
 #include <thread>
+#if defined(__linux__)
+#include <pthread.h>
+#include <sched.h>
+#endif
 #include <chrono>
 #include <deque>
 #include <map>
@@ -53,6 +57,7 @@ struct glio_marg_job {
   int W = 0;
   double eps = 1e-8;
   unsigned int epoch = 0;
+  int submit_cpu = -1;                 // CPU the submitting thread ran on (the worker keeps off it)
   std::vector<double> A, b;            // host-side accumulations (IMU / previous prior), marginalisation ordering
   std::vector<double> x0_pose, x0_sb;  // linearisation point of the kept states
   std::vector<double> out;             // snapshot of the device result (W x 28)
@@ -901,6 +906,11 @@ unsigned int marg_begin(glio_ctx* c, int W, const double* poses, const double* s
 
 void marg_worker(glio_ctx* c) {
   cudaSetDevice(c->device);
+#if defined(__linux__)
+  cpu_set_t base; CPU_ZERO(&base);
+  const bool have_base = pthread_getaffinity_np(pthread_self(), sizeof(base), &base) == 0;
+  int excluded = -1;
+#endif
   for (;;) {
     glio_marg_job* j = nullptr;
     {
@@ -909,6 +919,14 @@ void marg_worker(glio_ctx* c) {
       if (c->marg_quit && !c->marg_queued) return;
       j = c->marg_queued; c->marg_queued = nullptr;
     }
+#if defined(__linux__)
+    // The submitting thread is about to queue the next window's kernels: a worker woken onto ITS core would preempt it for the
+    // whole host half and the GPU would idle meanwhile.  Keep off that core (the rest of the process mask stays allowed).
+    if (have_base && j->submit_cpu >= 0 && j->submit_cpu != excluded && CPU_COUNT(&base) > 1) {
+      cpu_set_t m = base; CPU_CLR(j->submit_cpu, &m);
+      if (CPU_COUNT(&m) > 0 && pthread_setaffinity_np(pthread_self(), sizeof(m), &m) == 0) excluded = j->submit_cpu;
+    }
+#endif
     try {
       eval_unary_wait(c, j->epoch);
       j->out.assign(c->h_out.p, c->h_out.p + (size_t)j->W * GLIO_NACC);
@@ -956,6 +974,9 @@ int glio_window_marginalize_async(glio_ctx* c, int W, const double* poses, const
     j->ctx = c; j->W = W; j->eps = eps;
     j->x0_pose.assign(poses + 7, poses + 7 * (size_t)W); j->x0_sb.assign(speed_bias + 9, speed_bias + 18);
     j->epoch = marg_begin(c, W, poses, speed_bias, host_marg, user, j->A, j->b);
+#if defined(__linux__)
+    j->submit_cpu = sched_getcpu();
+#endif
     if (!c->marg_thread.joinable()) c->marg_thread = std::thread(marg_worker, c);
     { std::lock_guard<std::mutex> lk(c->marg_mu); c->marg_queued = j.get(); }
     c->marg_cv.notify_one();
