@@ -1,6 +1,7 @@
 // band_chol_test.cpp — the band Cholesky + solve of the host minimizer (glio::detail::cholesky_solve: portable path,
 // AVX2/FMA panel path, run-time dispatcher) against a dense reference on random SPD band matrices, including the window
-// shape (n = 300, hb = 29), the batch shape (wide band), tiny and degenerate sizes, and a non-positive-definite input.
+// shape (n = 300, hb = 29), the batch shapes (n = 2400, hb = 41; wide band), tiny and degenerate sizes, and a non-positive-definite
+// input; and the AVX2 band matrix-vector product (glio::detail::symv_avx2) against the dense product on the same matrices.
 #include <cmath>
 #include <cstdio>
 #include <random>
@@ -28,7 +29,7 @@ static bool dense_solve(const BandMat& A, const std::vector<double>& b, std::vec
 int main() {
   std::mt19937_64 rng(11); std::normal_distribution<double> N(0, 1);
   int bad = 0, cases = 0;
-  const int shapes[][2] = {{300, 29}, {300, 29}, {1200, 83}, {90, 89}, {17, 3}, {9, 8}, {8, 4}, {7, 6}, {5, 0}, {3, 2}, {1, 0}, {64, 1}, {33, 31}, {150, 14}, {6, 5}};
+  const int shapes[][2] = {{300, 29}, {300, 29}, {2400, 41}, {1200, 83}, {90, 89}, {17, 3}, {9, 8}, {8, 4}, {7, 6}, {5, 0}, {3, 2}, {1, 0}, {64, 1}, {33, 31}, {150, 14}, {6, 5}};
   for (auto& sh : shapes) {
     const int n = sh[0], hb = std::min(sh[1], std::max(n - 1, 0));
     BandMat L0; L0.reset(n, hb);
@@ -49,10 +50,21 @@ int main() {
 #else
     xa = xs;
 #endif
+    // y = A x: AVX2 band product against the dense one
+    double ey = 0, ny = 1e-300;
+#if defined(__x86_64__)
+    if (have_avx2) {
+      std::vector<double> xv(n), yr(n, 0.0), ya(n, -7.0);
+      for (double& v : xv) v = N(rng);
+      for (int i = 0; i < n; ++i) { double s = 0; for (int j = std::max(0, i - hb); j <= std::min(n - 1, i + hb); ++j) s += A.sym(i, j) * xv[j]; yr[i] = s; }
+      glio::detail::symv_avx2(A, xv.data(), ya.data());
+      for (int i = 0; i < n; ++i) { ny = std::max(ny, std::fabs(yr[i])); ey = std::max(ey, std::fabs(ya[i] - yr[i])); }
+    }
+#endif
     double nx = 1e-300, es = 0, ed = 0, ea = 0;
     for (int i = 0; i < n; ++i) { nx = std::max(nx, std::fabs(xr[i])); es = std::max(es, std::fabs(xs[i] - xr[i])); ed = std::max(ed, std::fabs(xd[i] - xr[i])); ea = std::max(ea, std::fabs(xa[i] - xr[i])); }
-    const bool ok = okr && oks && okd && oka && es / nx < 1e-9 && ed / nx < 1e-9 && ea / nx < 1e-9;
-    printf("shape %d %d %s scalar %.2e dispatch %.2e avx2 %.2e (avx2 available %d)\n", n, hb, ok ? "ok" : "FAIL", es / nx, ed / nx, ea / nx, (int)have_avx2);
+    const bool ok = okr && oks && okd && oka && es / nx < 1e-9 && ed / nx < 1e-9 && ea / nx < 1e-9 && ey / ny < 1e-12;
+    printf("shape %d %d %s scalar %.2e dispatch %.2e avx2 %.2e symv %.2e (avx2 available %d)\n", n, hb, ok ? "ok" : "FAIL", es / nx, ed / nx, ea / nx, ey / ny, (int)have_avx2);
     bad += !ok; ++cases;
   }
   {  // not positive definite: every path must report failure

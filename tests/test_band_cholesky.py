@@ -1,5 +1,5 @@
-"""Band Cholesky of the host minimizer: portable path, AVX2/FMA panel path and the run-time dispatcher against a dense
-reference (tests/cpp/band_chol_test.cpp), also with the fast path disabled (GLIO_NO_AVX2=1)."""
+"""Band Cholesky of the host minimizer (portable path, AVX2/FMA panel path, run-time dispatcher) and the AVX2 band
+matrix-vector product against a dense reference (tests/cpp/band_chol_test.cpp), also with the fast path disabled (GLIO_NO_AVX2=1)."""
 import os
 import subprocess
 
@@ -15,4 +15,4 @@ def test_band_cholesky_paths(tmp_path):
         p = subprocess.run([exe], text=True, capture_output=True, env={**os.environ, **env})
         assert p.returncode == 0, p.stdout + p.stderr
         lines = p.stdout.splitlines()
-        assert lines[-1] == "cases 16 bad 0" and all(" ok" in l for l in lines[:-1]), p.stdout
+        assert lines[-1] == "cases 17 bad 0" and all(" ok" in l for l in lines[:-1]), p.stdout
