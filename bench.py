@@ -337,26 +337,67 @@ def microbench_run(torch, dist, local_rank, rank, world, peak, steps=10):
 # ----------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------
-def bind_to_gpu_numa_node(local_rank):
-    """One process per GPU, pinned to the CPUs NVML reports as local to that GPU: the step is a chain of short launches and
-    host-side waits on pinned memory, and a rank that floats to the other socket pays a remote hop on every one of them."""
+def share_of_cpus(cpus, n_share, idx, siblings=None):
+    """The idx-th of n_share disjoint parts of `cpus`, whole physical cores at a time (siblings: cpu -> iterable of the hardware
+    threads of its core).  Ranks whose GPUs hang off the same socket get disjoint cores, so one rank's worker thread can never
+    wake onto a core where another rank's launching thread spins."""
+    cpus = set(cpus)
+    if n_share <= 1 or len(cpus) < 2 * n_share:
+        return cpus
+    cores, seen = [], set()
+    for c in sorted(cpus):
+        if c in seen:
+            continue
+        core = {c} | ({int(x) for x in siblings(c)} & cpus if siblings else set())
+        seen |= core; cores.append(sorted(core))
+    if len(cores) < n_share:
+        return cpus
+    lo, hi = idx * len(cores) // n_share, (idx + 1) * len(cores) // n_share
+    return {c for core in cores[lo:hi] for c in core} or cpus
+
+
+def _thread_siblings(cpu):
+    with open(f"/sys/devices/system/cpu/cpu{cpu}/topology/thread_siblings_list") as f:
+        out = []
+        for part in f.read().strip().split(","):
+            a, _, b = part.partition("-")
+            out.extend(range(int(a), int(b or a) + 1))
+        return out
+
+
+def bind_to_gpu_numa_node(local_rank, n_local=1):
+    """One process per GPU, pinned to CPUs NVML reports as local to that GPU: the step is a chain of short launches and host-side
+    waits on pinned memory, and a rank that floats to the other socket pays a remote hop on every one of them.  Ranks that share
+    a socket split its physical cores between them (share_of_cpus).  Returns the number of CPUs the process is bound to."""
     try:
         import pynvml
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
-        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return len(cpus)
+        nwords = (os.cpu_count() + 63) // 64
+        vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+
+        def cpus_of(i):
+            j = int(vis[i]) if i < len(vis) and vis[i].isdigit() else i          # NVML numbers the physical devices
+            words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(j), nwords)
+            return frozenset(64 * k + b for k, w in enumerate(words) for b in range(64) if (w >> b) & 1)
+        mine = cpus_of(local_rank)
+        cpus = set(mine) & os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        try:
+            peers = [i for i in range(max(n_local, 1)) if cpus_of(i) == mine]
+            if local_rank in peers and len(peers) > 1:
+                cpus = share_of_cpus(cpus, len(peers), peers.index(local_rank), _thread_siblings)
+        except Exception:
+            pass
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
     except Exception:
         pass
     return None
 
 
 def run_glio(args, rank, world, local_rank):
-    n_bound = bind_to_gpu_numa_node(local_rank)
+    n_bound = bind_to_gpu_numa_node(local_rank, world)
     import torch
     from glio_b200 import api
     torch.cuda.set_device(local_rank)

@@ -119,3 +119,19 @@ def test_band_callback_rejects_a_too_narrow_band():
         rc = L.glio_hf_evaluate_band(hf._h, C.c_int(3), T.ctypes.data_as(C.c_void_p), sb.ctypes.data_as(C.c_void_p), C.c_int(1),
                                      Hb.ctypes.data_as(C.c_void_p), C.c_int(hb), g.ctypes.data_as(C.c_void_p), cost.ctypes.data_as(C.c_void_p))
         assert (rc == 0) == want_ok, (hb, rc)
+
+
+def test_bench_splits_a_socket_between_its_ranks_by_whole_cores():
+    """bench.py binds every rank to the CPUs local to its GPU; ranks behind the same socket get disjoint physical cores"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+    sib = lambda c: (c % 64, c % 64 + 64)                                  # 2 hardware threads per core: i and i + 64
+    socket0 = set(range(0, 32)) | set(range(64, 96))
+    parts = [b.share_of_cpus(socket0, 4, i, sib) for i in range(4)]
+    assert set().union(*parts) == socket0 and sum(len(p) for p in parts) == len(socket0)
+    for p in parts:
+        assert len(p) == 16 and all(set(sib(c)) <= p for c in p)
+    assert b.share_of_cpus({0, 1, 2}, 4, 1, sib) == {0, 1, 2}             # too few CPUs to split: left alone
+    assert b.share_of_cpus(socket0, 1, 0, sib) == socket0
+    assert b.share_of_cpus(socket0, 3, 2, None) == set(sorted(socket0)[42:])   # no topology information: plain thirds
