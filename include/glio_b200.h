@@ -290,7 +290,9 @@ int glio_window_marginalize(glio_ctx* ctx, int W, const double* poses, const dou
  * context: the call returns when the device half is queued and host_marg has run, so the caller can hand the NEXT window's map and
  * association to the GPU meanwhile (the reference does these strictly one after the other, Estimator.cpp:2462-2608 then the next
  * processImage).  One job at a time per context.  glio_marg_job_wait joins the job, frees it and returns the prior (identical to
- * glio_window_marginalize's); call it before the next solve needs the prior.  glio_destroy joins an abandoned job. */
+ * glio_window_marginalize's); call it before the next solve needs the prior.  glio_destroy joins AND frees an abandoned job: a job
+ * handle must not be used after its context is gone.  A context is otherwise single-threaded: calls on one context must not
+ * overlap, the worker is the library's own. */
 typedef struct glio_marg_job glio_marg_job;
 int glio_window_marginalize_async(glio_ctx* ctx, int W, const double* poses, const double* speed_bias, glio_host_marg_fn host_marg,
                                   void* user, double eps, glio_marg_job** job_out);
